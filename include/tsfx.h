@@ -1,0 +1,210 @@
+/* tsfx.h -- C ABI of libtsfx.so: the B200 (sm_100a) implementation of tsfresh's feature-extraction
+ * hot path.
+ *
+ * There is no native interface in the reference (tsfresh is pure Python); the entry points below are
+ * what a ctypes binding for the path replaces:
+ *
+ *   tsfx_plan_create      <- the settings dict walked by _do_extraction_on_chunk
+ *                            (tsfresh/feature_extraction/extraction.py:339-378, settings.py:133-294):
+ *                            one tsfx_feature_desc per output column, in column order.
+ *   tsfx_extract_csr      <- _do_extraction_on_chunk over every (id, kind) series of a chunk list
+ *   tsfx_extract_dense       (extraction.py:308-386; distribution.py:173-245 map_reduce): all series in
+ *                            one call, results as the dense [n_series x n_features] float64 matrix that
+ *                            PartitionedTsData.pivot (data.py:86-121) would assemble.
+ *   tsfx_extract_long     <- LongTsFrameAdapter / WideTsFrameAdapter iteration (data.py:181-291):
+ *                            group by id, sort each group by the sort column, then the above.
+ *   tsfx_roll_windows     <- roll_time_series window enumeration
+ *                            (utilities/dataframe_functions.py:376-603), expressed as CSR views.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Return 0 on success, a negative TSFX_E_*
+ * code otherwise (text via tsfx_last_error).  The caller owns every buffer it passes; the library owns
+ * only the device scratch inside the context.  Pointers are host pointers unless TSFX_FLAG_DEVICE_PTRS
+ * is set, in which case `values`, `begin`, `len` and `out` are device pointers on the context's device
+ * and the call is asynchronous on the context's stream (use tsfx_sync).  NaN results that the
+ * reference defines (short series, zero variance, ...) are values, not errors.  Values are float32
+ * (BASELINE.json north_star); all arithmetic is float64.
+ */
+#ifndef TSFX_H_
+#define TSFX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSFX_VERSION 1
+
+/* error codes */
+#define TSFX_OK 0
+#define TSFX_E_INVALID (-1)     /* bad argument / malformed plan */
+#define TSFX_E_CUDA (-2)        /* CUDA runtime failure (message has the cudaError string) */
+#define TSFX_E_UNSUPPORTED (-3) /* parameter combination without a GPU implementation */
+#define TSFX_E_TOO_LONG (-4)    /* a series does not fit the per-warp shared-memory staging */
+#define TSFX_E_NOMEM (-5)
+#define TSFX_E_NAN (-6)         /* NaN in the value column (data.py:148-167 raises ValueError) */
+
+/* flags */
+#define TSFX_FLAG_DEVICE_PTRS 1u /* values/begin/len/out are device pointers; async on ctx stream */
+#define TSFX_FLAG_TIMING 2u      /* record CUDA events around every kernel group (tsfx_get_timings) */
+#define TSFX_FLAG_NO_NAN_CHECK 4u
+
+/* calculator ids: one per reference calculator (feature_calculators.py line in the comment) */
+enum tsfx_calc {
+    TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION = 0, /* :239 */
+    TSFX_RATIO_BEYOND_R_SIGMA,                         /* :256  p0=r */
+    TSFX_LARGE_STANDARD_DEVIATION,                     /* :273  p0=r */
+    TSFX_SYMMETRY_LOOKING,                             /* :299  p0=r */
+    TSFX_HAS_DUPLICATE_MAX,                            /* :325 */
+    TSFX_HAS_DUPLICATE_MIN,                            /* :340 */
+    TSFX_HAS_DUPLICATE,                                /* :355 */
+    TSFX_SUM_VALUES,                                   /* :371 */
+    TSFX_AGG_AUTOCORRELATION,                          /* :387  attr=f_agg i0=maxlag */
+    TSFX_PARTIAL_AUTOCORRELATION,                      /* :440  i0=lag i1=max lag over the param list */
+    TSFX_AUGMENTED_DICKEY_FULLER,                      /* :499  attr=teststat|pvalue|usedlag i0=autolag */
+    TSFX_ABS_ENERGY,                                   /* :548 */
+    TSFX_CID_CE,                                       /* :567  i0=normalize */
+    TSFX_MEAN_ABS_CHANGE,                              /* :604 */
+    TSFX_MEAN_CHANGE,                                  /* :624 */
+    TSFX_MEAN_SECOND_DERIVATIVE_CENTRAL,               /* :644 */
+    TSFX_MEDIAN,                                       /* :663 */
+    TSFX_MEAN,                                         /* :677 */
+    TSFX_LENGTH,                                       /* :691 */
+    TSFX_STANDARD_DEVIATION,                           /* :705 */
+    TSFX_VARIATION_COEFFICIENT,                        /* :718 */
+    TSFX_VARIANCE,                                     /* :735 */
+    TSFX_SKEWNESS,                                     /* :749 */
+    TSFX_KURTOSIS,                                     /* :766 */
+    TSFX_ROOT_MEAN_SQUARE,                             /* :783 */
+    TSFX_ABSOLUTE_SUM_OF_CHANGES,                      /* :796 */
+    TSFX_LONGEST_STRIKE_BELOW_MEAN,                    /* :813 */
+    TSFX_LONGEST_STRIKE_ABOVE_MEAN,                    /* :828 */
+    TSFX_COUNT_ABOVE_MEAN,                             /* :843 */
+    TSFX_COUNT_BELOW_MEAN,                             /* :857 */
+    TSFX_LAST_LOCATION_OF_MAXIMUM,                     /* :871 */
+    TSFX_FIRST_LOCATION_OF_MAXIMUM,                    /* :886 */
+    TSFX_LAST_LOCATION_OF_MINIMUM,                     /* :902 */
+    TSFX_FIRST_LOCATION_OF_MINIMUM,                    /* :917 */
+    TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES,         /* :933 */
+    TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS, /* :961 */
+    TSFX_SUM_OF_REOCCURRING_VALUES,                    /* :992 */
+    TSFX_SUM_OF_REOCCURRING_DATA_POINTS,               /* :1020 */
+    TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH,     /* :1045 */
+    TSFX_FFT_COEFFICIENT,                              /* :1067 attr=real|imag|abs|angle i0=coeff */
+    TSFX_FFT_AGGREGATED,                               /* :1123 attr=centroid|variance|skew|kurtosis */
+    TSFX_NUMBER_PEAKS,                                 /* :1235 i0=n */
+    TSFX_INDEX_MASS_QUANTILE,                          /* :1275 p0=q */
+    TSFX_NUMBER_CWT_PEAKS,                             /* :1320 i0=n */
+    TSFX_LINEAR_TREND,                                 /* :1343 attr=pvalue|rvalue|intercept|slope|stderr */
+    TSFX_CWT_COEFFICIENTS,                             /* :1370 i0=coeff i1=table index of scale w */
+    TSFX_SPKT_WELCH_DENSITY,                           /* :1418 i0=coeff */
+    TSFX_AR_COEFFICIENT,                               /* :1459 i0=coeff i1=k */
+    TSFX_CHANGE_QUANTILES,                             /* :1511 p0=ql p1=qh i0=isabs attr=f_agg */
+    TSFX_TIME_REVERSAL_ASYMMETRY_STATISTIC,            /* :1557 i0=lag */
+    TSFX_C3,                                           /* :1600 i0=lag */
+    TSFX_MEAN_N_ABSOLUTE_MAX,                          /* :1643 i0=number_of_maxima */
+    TSFX_BINNED_ENTROPY,                               /* :1666 i0=max_bins */
+    TSFX_SAMPLE_ENTROPY,                               /* :1701 */
+    TSFX_APPROXIMATE_ENTROPY,                          /* :1759 i0=m p0=r */
+    TSFX_FOURIER_ENTROPY,                              /* :1809 i0=bins */
+    TSFX_LEMPEL_ZIV_COMPLEXITY,                        /* :1825 i0=bins */
+    TSFX_PERMUTATION_ENTROPY,                          /* :1866 i0=tau i1=dimension */
+    TSFX_AUTOCORRELATION,                              /* :1919 i0=lag */
+    TSFX_QUANTILE,                                     /* :1963 p0=q */
+    TSFX_NUMBER_CROSSING_M,                            /* :1980 p0=m */
+    TSFX_MAXIMUM,                                      /* :2003 */
+    TSFX_ABSOLUTE_MAXIMUM,                             /* :2017 */
+    TSFX_MINIMUM,                                      /* :2031 */
+    TSFX_VALUE_COUNT,                                  /* :2044 p0=value */
+    TSFX_RANGE_COUNT,                                  /* :2065 p0=min p1=max */
+    TSFX_FRIEDRICH_COEFFICIENTS,                       /* :2082 i0=coeff i1=m i2=r */
+    TSFX_MAX_LANGEVIN_FIXED_POINT,                     /* :2134 i1=m i2=r */
+    TSFX_AGG_LINEAR_TREND,                             /* :2171 attr=linregress attr i0=chunk_len i1=f_agg */
+    TSFX_ENERGY_RATIO_BY_CHUNKS,                       /* :2226 i0=num_segments i1=segment_focus */
+    TSFX_COUNT_ABOVE,                                  /* :2309 p0=t */
+    TSFX_COUNT_BELOW,                                  /* :2325 p0=t */
+    TSFX_BENFORD_CORRELATION,                          /* :2341 */
+    TSFX_QUERY_SIMILARITY_COUNT,                       /* :2475 default query=None -> NaN */
+    TSFX_CONST_NAN,                                    /* a column the reference defines as NaN */
+    TSFX_N_CALCS
+};
+
+/* attr codes */
+enum { TSFX_AGG_MEAN = 0, TSFX_AGG_MEDIAN, TSFX_AGG_VAR, TSFX_AGG_STD, TSFX_AGG_MAX, TSFX_AGG_MIN };
+enum { TSFX_FFT_REAL = 0, TSFX_FFT_IMAG, TSFX_FFT_ABS, TSFX_FFT_ANGLE };
+enum { TSFX_SPEC_CENTROID = 0, TSFX_SPEC_VARIANCE, TSFX_SPEC_SKEW, TSFX_SPEC_KURTOSIS };
+enum { TSFX_LR_PVALUE = 0, TSFX_LR_RVALUE, TSFX_LR_INTERCEPT, TSFX_LR_SLOPE, TSFX_LR_STDERR };
+enum { TSFX_ADF_TESTSTAT = 0, TSFX_ADF_PVALUE, TSFX_ADF_USEDLAG, TSFX_ADF_BADATTR };
+enum { TSFX_AUTOLAG_AIC = 0, TSFX_AUTOLAG_BIC, TSFX_AUTOLAG_NONE };
+
+/* One output column. `col` is its index in the row-major [n_series x n_cols] result. */
+typedef struct tsfx_feature_desc {
+    int32_t calc; /* enum tsfx_calc */
+    int32_t attr;
+    int32_t i0, i1, i2;
+    int32_t col;
+    double p0, p1;
+} tsfx_feature_desc;
+
+typedef struct tsfx_ctx tsfx_ctx;
+typedef struct tsfx_plan tsfx_plan;
+
+/* Context: one per process and device.  `cuda_stream` may be NULL (library creates its own stream) or
+ * a cudaStream_t the caller owns (e.g. torch's current stream) so caller-side CUDA events see the work. */
+int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out);
+void tsfx_ctx_destroy(tsfx_ctx* ctx);
+const char* tsfx_last_error(const tsfx_ctx* ctx); /* ctx may be NULL: last creation error */
+int tsfx_sync(tsfx_ctx* ctx);
+int tsfx_version(void);
+
+/* Plan: the compiled settings dict.  `tables` holds the concatenated float64 convolution kernels for
+ * cwt_coefficients (one per distinct scale, table t = tables[table_off[t] .. table_off[t+1])),
+ * scaled so that coefficient c of scale t is sum_k x[k] * table_t[c + half_t - k]; `table_half[t]` is
+ * half_t.  n_cols is the row stride of the output (>= max col + 1). */
+int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, int32_t n_descs, int32_t n_cols,
+                     const double* tables, const int64_t* table_off, const int32_t* table_half,
+                     int32_t n_tables, tsfx_plan** out);
+void tsfx_plan_destroy(tsfx_plan* plan);
+
+/* CSR: series s is values[begin[s] .. begin[s]+len[s]).  out is [n_series x n_cols] float64 row-major. */
+int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_values,
+                     const int64_t* begin, const int32_t* len, int64_t n_series, double* out,
+                     uint32_t flags);
+
+/* Dense fast path: n_series series of identical length `len`, back to back. */
+int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_series,
+                       int32_t len, double* out, uint32_t flags);
+
+/* Long frame (stage (a)): rows (ids[i], sort_keys[i], values[i]) in any order.  Groups rows by id,
+ * orders each group by sort key (stable for equal keys; sort_keys may be NULL = keep row order), then
+ * extracts.  Series come out in ascending id order: out_ids[s] and row s of out.  Host pointers only.
+ * sort_key_is_f64: 0 = int64 keys, 1 = float64 keys.  Returns the number of series in *n_series_out;
+ * TSFX_E_INVALID if it exceeds out_capacity. */
+int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
+                      int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t* out_ids,
+                      double* out, int64_t out_capacity, int64_t* n_series_out, uint32_t flags);
+
+/* Stage (a) alone: builds the CSR on the device and copies it back (sorted_values may be NULL). */
+int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sort_keys, int32_t sort_key_is_f64,
+                   const float* values, int64_t n_rows, int64_t* out_ids, int64_t* out_begin,
+                   int32_t* out_len, float* sorted_values, int64_t out_capacity, int64_t* n_series_out);
+
+/* roll_time_series as views: for every series s of the input CSR and every window end t
+ * (dataframe_functions.py:340-373, positive rolling_direction), emits win_begin/win_len over the SAME
+ * values buffer plus (parent, t_end_index).  Returns the number of windows (or a negative error);
+ * pass NULL outputs to only count. */
+int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, int64_t n_series,
+                          int32_t rolling_direction, int32_t max_timeshift, int32_t min_timeshift,
+                          int64_t* win_begin, int32_t* win_len, int64_t* win_parent,
+                          int32_t* win_end_index, int64_t capacity);
+
+/* Per-kernel-group device time (ms) of the last extract call made with TSFX_FLAG_TIMING.
+ * names_out[i] points at a static string.  Returns the number of groups written (<= cap). */
+int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names_out, int32_t cap);
+/* Number of kernels the last extract call launched. */
+int tsfx_last_launch_count(const tsfx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSFX_H_ */
