@@ -1,0 +1,234 @@
+"""ctypes binding of libtsfx.so (include/tsfx.h).  There is no fallback: if the library is missing or
+cannot create a context on a CUDA device, every entry point raises."""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from .plan import DESC_DTYPE, Plan
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtsfx.so")
+
+FLAG_DEVICE_PTRS = 1
+FLAG_TIMING = 2
+
+_ERR = {-1: ValueError, -2: RuntimeError, -3: NotImplementedError, -4: ValueError, -5: MemoryError, -6: ValueError}
+
+_lib = None
+_lock = threading.Lock()
+
+EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync", "tsfx_version",
+           "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
+           "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
+           "tsfx_last_launch_count"]
+
+
+def load():
+    """Loads (building first when nvcc and the sources are newer) and returns the ctypes library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
+        lib.tsfx_ctx_create.argtypes = [ctypes.c_int, vp, ctypes.POINTER(vp)]
+        lib.tsfx_ctx_destroy.argtypes = [vp]
+        lib.tsfx_ctx_destroy.restype = None
+        lib.tsfx_last_error.argtypes = [vp]
+        lib.tsfx_last_error.restype = ctypes.c_char_p
+        lib.tsfx_sync.argtypes = [vp]
+        lib.tsfx_plan_create.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, ctypes.POINTER(vp)]
+        lib.tsfx_plan_destroy.argtypes = [vp]
+        lib.tsfx_plan_destroy.restype = None
+        lib.tsfx_extract_csr.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, u32]
+        lib.tsfx_extract_dense.argtypes = [vp, vp, vp, i64, i32, vp, u32]
+        lib.tsfx_extract_long.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, vp, i64, ctypes.POINTER(i64), u32]
+        lib.tsfx_build_csr.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, i64, ctypes.POINTER(i64)]
+        lib.tsfx_roll_windows.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, i64]
+        lib.tsfx_roll_windows.restype = i64
+        lib.tsfx_get_timings.argtypes = [vp, vp, vp, i32]
+        lib.tsfx_last_launch_count.argtypes = [vp]
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One per process and device (tsfx_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        rc = self.lib.tsfx_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h))
+        if rc != 0:
+            raise _ERR.get(rc, RuntimeError)("tsfx_ctx_create: " + self.lib.tsfx_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self._plans = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in list(self._plans.values()):
+                p.close()
+            self._plans.clear()
+            self.lib.tsfx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise _ERR.get(rc, RuntimeError)("%s: %s" % (what, self.lib.tsfx_last_error(self.h).decode()))
+
+    def sync(self):
+        self.check(self.lib.tsfx_sync(self.h), "tsfx_sync")
+
+    def timings(self):
+        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 16)()
+        k = self.lib.tsfx_get_timings(self.h, ms, names, 16)
+        if k < 0:
+            self.check(k, "tsfx_get_timings")
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+    def launch_count(self):
+        return int(self.lib.tsfx_last_launch_count(self.h))
+
+
+class DevicePlan:
+    """tsfx_plan: the compiled settings on one context."""
+
+    def __init__(self, ctx, plan):
+        assert isinstance(plan, Plan)
+        self.ctx, self.plan = ctx, plan
+        self.n_cols = plan.n_cols
+        tables, off, half = plan.cwt_tables()
+        descs = np.ascontiguousarray(plan.descs, dtype=DESC_DTYPE)
+        h = ctypes.c_void_p()
+        rc = ctx.lib.tsfx_plan_create(ctx.h, _ptr(descs), len(descs), plan.n_cols, _ptr(tables), _ptr(off),
+                                      _ptr(half), len(half), ctypes.byref(h))
+        ctx.check(rc, "tsfx_plan_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.tsfx_plan_destroy(self.h)
+            self.h = None
+
+    # ---- host-pointer entry points -------------------------------------------------------------
+    def extract_csr(self, values, begin, length, flags=0):
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        begin = np.ascontiguousarray(begin, dtype=np.int64)
+        length = np.ascontiguousarray(length, dtype=np.int32)
+        out = np.empty((len(begin), self.n_cols), dtype=np.float64)
+        rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, _ptr(values), values.size, _ptr(begin), _ptr(length),
+                                           len(begin), _ptr(out), flags)
+        self.ctx.check(rc, "tsfx_extract_csr")
+        return out
+
+    def extract_dense(self, values2d, flags=0, out=None):
+        values2d = np.ascontiguousarray(values2d, dtype=np.float32)
+        n, L = values2d.shape
+        if out is None:
+            out = np.empty((n, self.n_cols), dtype=np.float64)
+        rc = self.ctx.lib.tsfx_extract_dense(self.ctx.h, self.h, _ptr(values2d), n, L, _ptr(out), flags)
+        self.ctx.check(rc, "tsfx_extract_dense")
+        return out
+
+    def extract_long(self, ids, sort_keys, values, flags=0):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        is_f64 = 0
+        if sort_keys is not None:
+            sort_keys = np.asarray(sort_keys)
+            if sort_keys.dtype.kind == "f":
+                sort_keys = np.ascontiguousarray(sort_keys, dtype=np.float64)
+                is_f64 = 1
+            else:
+                sort_keys = np.ascontiguousarray(sort_keys, dtype=np.int64)
+        cap = len(ids)
+        out_ids = np.empty(cap, dtype=np.int64)
+        # the number of series is not known before the device pass: size for the worst case lazily
+        n_series = ctypes.c_int64(0)
+        out = np.empty((0, self.n_cols))
+        # first call with capacity 0 only counts when the frame is large; small frames go straight
+        guess = cap if cap * self.n_cols <= (1 << 24) else 0
+        out = np.empty((guess, self.n_cols), dtype=np.float64)
+        rc = self.ctx.lib.tsfx_extract_long(self.ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids),
+                                            _ptr(out_ids), _ptr(out) if guess else _ptr(np.empty(1)), guess,
+                                            ctypes.byref(n_series), flags)
+        if rc == -1 and n_series.value > guess:
+            out = np.empty((n_series.value, self.n_cols), dtype=np.float64)
+            rc = self.ctx.lib.tsfx_extract_long(self.ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values),
+                                                len(ids), _ptr(out_ids), _ptr(out), n_series.value,
+                                                ctypes.byref(n_series), flags)
+        self.ctx.check(rc, "tsfx_extract_long")
+        k = n_series.value
+        return out_ids[:k].copy(), out[:k]
+
+    # ---- device-pointer entry points (torch tensors own the memory) ----------------------------
+    def extract_dense_device(self, values_ptr, n_series, length, out_ptr, timing=False):
+        flags = FLAG_DEVICE_PTRS | (FLAG_TIMING if timing else 0)
+        rc = self.ctx.lib.tsfx_extract_dense(self.ctx.h, self.h, ctypes.c_void_p(values_ptr), n_series, length,
+                                             ctypes.c_void_p(out_ptr), flags)
+        self.ctx.check(rc, "tsfx_extract_dense")
+
+    def extract_csr_device(self, values_ptr, n_values, begin_ptr, len_ptr, n_series, out_ptr, timing=False):
+        flags = FLAG_DEVICE_PTRS | (FLAG_TIMING if timing else 0)
+        rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, ctypes.c_void_p(values_ptr), n_values,
+                                           ctypes.c_void_p(begin_ptr), ctypes.c_void_p(len_ptr), n_series,
+                                           ctypes.c_void_p(out_ptr), flags)
+        self.ctx.check(rc, "tsfx_extract_csr")
+
+
+def build_csr(ctx, ids, sort_keys, values):
+    """Stage (a) alone: returns (unique_ids, begin, len, values_in_series_order)."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    values = np.ascontiguousarray(values, dtype=np.float32)
+    is_f64 = 0
+    if sort_keys is not None:
+        sort_keys = np.asarray(sort_keys)
+        if sort_keys.dtype.kind == "f":
+            sort_keys = np.ascontiguousarray(sort_keys, dtype=np.float64)
+            is_f64 = 1
+        else:
+            sort_keys = np.ascontiguousarray(sort_keys, dtype=np.int64)
+    n = len(ids)
+    uid = np.empty(n, dtype=np.int64)
+    begin = np.empty(n, dtype=np.int64)
+    length = np.empty(n, dtype=np.int32)
+    sv = np.empty(n, dtype=np.float32)
+    k = ctypes.c_int64(0)
+    rc = ctx.lib.tsfx_build_csr(ctx.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), n, _ptr(uid), _ptr(begin),
+                                _ptr(length), _ptr(sv), n, ctypes.byref(k))
+    ctx.check(rc, "tsfx_build_csr")
+    k = k.value
+    return uid[:k].copy(), begin[:k].copy(), length[:k].copy(), sv
+
+
+def roll_windows(begin, length, rolling_direction, max_timeshift, min_timeshift):
+    lib = load()
+    begin = np.ascontiguousarray(begin, dtype=np.int64)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    k = lib.tsfx_roll_windows(_ptr(begin), _ptr(length), len(begin), rolling_direction, max_timeshift, min_timeshift,
+                              None, None, None, None, 0)
+    if k < 0:
+        raise ValueError("tsfx_roll_windows: invalid arguments")
+    wb, wl = np.empty(k, dtype=np.int64), np.empty(k, dtype=np.int32)
+    wp, we = np.empty(k, dtype=np.int64), np.empty(k, dtype=np.int32)
+    k2 = lib.tsfx_roll_windows(_ptr(begin), _ptr(length), len(begin), rolling_direction, max_timeshift, min_timeshift,
+                               _ptr(wb), _ptr(wl), _ptr(wp), _ptr(we), k)
+    assert k2 == k
+    return wb, wl, wp, we

@@ -1,0 +1,621 @@
+// k_basic.cu -- kernel group BASIC: moments / extrema / counts / order-dependent streams.
+//
+// One warp per series.  Shared memory per warp: xs[npad] float32 (the series as ingested),
+// xc[npad] float64 (centred copy x - mean), scr[nscr] float64 (scratch: chunk aggregates, histograms),
+// lagS[nlag] float64 (lag products).  Calculators restated (feature_calculators.py line numbers in
+// include/tsfx.h): every "class M" and "class O" row of SURVEY.md section 8a.
+#include "tsfx_common.cuh"
+#include "tsfx_math.cuh"
+#include "tsfx_kernels.h"
+#include <algorithm>
+
+namespace tsfx {
+
+struct Extra {
+    double m3, m4;            // sum (x-mean)^3, ^4
+    int cnt_above, cnt_below; // x > mean, x < mean
+    int cnt_min, cnt_max, first_min, last_min, first_max, last_max;
+    double sad, ssd;          // sum |dx|, sum dx^2
+    int strike_above, strike_below;
+};
+
+struct Run { int len, pre, suf, best; };
+
+__device__ __forceinline__ Run run_of_word(unsigned w, int bits) {
+    // `bits` valid low bits (bits beyond are zero)
+    Run r;
+    r.len = bits;
+    if (bits == 0) { r.pre = r.suf = r.best = 0; return r; }
+    unsigned full = (bits == 32) ? 0xffffffffu : ((1u << bits) - 1u);
+    if (w == full) { r.pre = r.suf = r.best = bits; return r; }
+    r.pre = __ffs(~w) - 1;
+    unsigned top = w << (32 - bits);                 // align the valid bits to the top
+    r.suf = __clz(~top);
+    int b = 0;
+    unsigned t = w;
+    while (t) { t &= (t << 1); ++b; }
+    r.best = b;
+    return r;
+}
+__device__ __forceinline__ Run run_combine(const Run& a, const Run& b) {
+    Run r;
+    r.len = a.len + b.len;
+    r.pre = (a.pre == a.len) ? a.len + b.pre : a.pre;
+    r.suf = (b.suf == b.len) ? b.len + a.suf : b.suf;
+    r.best = max(max(a.best, b.best), a.suf + b.pre);
+    return r;
+}
+// longest run of set bits over per-lane words (lane 0 first); result valid in all lanes
+__device__ __forceinline__ Run run_warp(Run r) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Run other;
+        other.len = __shfl_down_sync(FULL, r.len, o);
+        other.pre = __shfl_down_sync(FULL, r.pre, o);
+        other.suf = __shfl_down_sync(FULL, r.suf, o);
+        other.best = __shfl_down_sync(FULL, r.best, o);
+        int lane = threadIdx.x & 31;
+        if (lane + o < 32) r = run_combine(r, other);
+    }
+    Run out;
+    out.len = __shfl_sync(FULL, r.len, 0);
+    out.pre = __shfl_sync(FULL, r.pre, 0);
+    out.suf = __shfl_sync(FULL, r.suf, 0);
+    out.best = __shfl_sync(FULL, r.best, 0);
+    return out;
+}
+
+__device__ __forceinline__ Extra extra_pass(const float* xs, const double* xc, int n, const Moments& M, int lane) {
+    Extra E;
+    double a3 = 0.0, a4 = 0.0, sad = 0.0, ssd = 0.0;
+    int ca = 0, cb = 0, cmin = 0, cmax = 0;
+    int fmin_i = 0x7fffffff, lmin_i = -1, fmax_i = 0x7fffffff, lmax_i = -1;
+    const float fl = (float)M.vmin, fh = (float)M.vmax;
+    Run ra = {0, 0, 0, 0}, rb = {0, 0, 0, 0};
+    Run acc_a = {0, 0, 0, 0}, acc_b = {0, 0, 0, 0};
+    unsigned wa = 0, wb = 0;
+    int wbits = 0;
+    int tile = 0;
+    for (int base = 0; base < n; base += 32, ++tile) {
+        int i = base + lane;
+        bool ok = i < n;
+        double d = ok ? xc[i] : 0.0;
+        float f = ok ? xs[i] : 0.f;
+        double d2 = d * d;
+        a3 = fma(d2, d, a3);
+        a4 = fma(d2, d2, a4);
+        bool above = ok && d > 0.0, below = ok && d < 0.0;
+        unsigned ma = __ballot_sync(FULL, above), mb = __ballot_sync(FULL, below);
+        ca += __popc(ma);
+        cb += __popc(mb);
+        if ((tile & 31) == lane) { wa = ma; wb = mb; wbits = min(32, n - base); }
+        if (ok && f == fl) { ++cmin; fmin_i = min(fmin_i, i); lmin_i = i; }
+        if (ok && f == fh) { ++cmax; fmax_i = min(fmax_i, i); lmax_i = i; }
+        if (i + 1 < n) {
+            double dx = (double)xs[i + 1] - (double)f;
+            sad += fabs(dx);
+            ssd = fma(dx, dx, ssd);
+        }
+        if ((tile & 31) == 31 || base + 32 >= n) {      // flush a super-tile of up to 32 words
+            ra = run_warp(run_of_word(wa, wbits));
+            rb = run_warp(run_of_word(wb, wbits));
+            acc_a = run_combine(acc_a, ra);
+            acc_b = run_combine(acc_b, rb);
+            wa = wb = 0; wbits = 0;
+        }
+    }
+    E.m3 = wsum(a3);
+    E.m4 = wsum(a4);
+    E.sad = wsum(sad);
+    E.ssd = wsum(ssd);
+    E.cnt_above = ca;
+    E.cnt_below = cb;
+    E.cnt_min = wsumi(cmin);
+    E.cnt_max = wsumi(cmax);
+    E.first_min = wmini(fmin_i);
+    E.last_min = wmaxi(lmin_i);
+    E.first_max = wmini(fmax_i);
+    E.last_max = wmaxi(lmax_i);
+    E.strike_above = acc_a.best;
+    E.strike_below = acc_b.best;
+    return E;
+}
+
+// sum_{t < n-k} xc[t] * xc[t+k]
+__device__ __forceinline__ double lag_product(const double* xc, int n, int k, int lane) {
+    double a = 0.0;
+    for (int i = lane; i + k < n; i += 32) a = fma(xc[i], xc[i + k], a);
+    return wsum(a);
+}
+
+// numpy histogram bin index for uniform bins (numpy/lib/_histograms_impl.py fast path)
+__device__ __forceinline__ int hist_bin(double v, double first, double last, double denom, double step, int nb) {
+    double f = __dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), (double)nb);
+    int idx = (int)f;
+    if (idx == nb) idx -= 1;
+    // edge(i) = i*step + first, edge(nb) = last  (np.linspace)
+    double e_lo = (idx == nb) ? last : __dadd_rn(__dmul_rn((double)idx, step), first);
+    if (v < e_lo) idx -= 1;
+    double e_hi = (idx + 1 == nb) ? last : __dadd_rn(__dmul_rn((double)(idx + 1), step), first);
+    if (v >= e_hi && idx != nb - 1) idx += 1;
+    return idx;
+}
+
+// -sum p ln p of an int histogram in shared memory (hist[0..nb)), total count n
+__device__ __forceinline__ double hist_entropy(const int* hist, int nb, int n, int lane) {
+    double a = 0.0;
+    for (int b = lane; b < nb; b += 32) {
+        int c = hist[b];
+        if (c > 0) {
+            double p = (double)c / (double)n;
+            a += p * log(p);
+        }
+    }
+    return -wsum(a);
+}
+
+// binned entropy of `cnt` values produced by f(i) (np.histogram(x, bins) -> -sum p ln p)
+template <typename F>
+__device__ __forceinline__ double binned_entropy_of(F val, int cnt, double vmin, double vmax, int nb,
+                                                    int* hist, int lane) {
+    double first = vmin, last = vmax;
+    if (first == last) { first -= 0.5; last += 0.5; }
+    double denom = __dsub_rn(last, first);
+    double step = __ddiv_rn(denom, (double)nb);
+    for (int b = lane; b < nb; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+        int idx = hist_bin(val(i), first, last, denom, step, nb);
+        atomicAdd(&hist[idx], 1);
+    }
+    __syncwarp();
+    double h = hist_entropy(hist, nb, cnt, lane);
+    __syncwarp();
+    return h;
+}
+
+__device__ __forceinline__ double agg_chunk(const float* xs, int lo, int hi, int f_agg) {
+    // ndarray.max/min/mean/var/std/median over xs[lo:hi) by one lane (_aggregate_on_chunks :176-193)
+    int c = hi - lo;
+    if (f_agg == TSFX_AGG_MAX) { float m = xs[lo]; for (int i = lo + 1; i < hi; ++i) m = fmaxf(m, xs[i]); return (double)m; }
+    if (f_agg == TSFX_AGG_MIN) { float m = xs[lo]; for (int i = lo + 1; i < hi; ++i) m = fminf(m, xs[i]); return (double)m; }
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += (double)xs[i];
+    double mu = s / (double)c;
+    if (f_agg == TSFX_AGG_MEAN) return mu;
+    if (f_agg == TSFX_AGG_MEDIAN) {
+        // rank selection without modifying the data (chunks are short)
+        int k1 = (c - 1) / 2, k2 = c / 2;
+        double v1 = 0.0, v2 = 0.0;
+        for (int i = lo; i < hi; ++i) {
+            float xi = xs[i];
+            int r = 0;
+            for (int j = lo; j < hi; ++j) r += (xs[j] < xi) || (xs[j] == xi && j < i);
+            if (r == k1) v1 = (double)xi;
+            if (r == k2) v2 = (double)xi;
+        }
+        return 0.5 * (v1 + v2);
+    }
+    double q = 0.0;
+    for (int i = lo; i < hi; ++i) { double d = (double)xs[i] - mu; q = fma(d, d, q); }
+    double v = q / (double)c;
+    return f_agg == TSFX_AGG_STD ? sqrt(v) : v;
+}
+
+// linregress(range(k), y[0..k)) with y in shared memory
+__device__ __forceinline__ LinReg linreg_index(const double* y, int k, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < k; i += 32) s += y[i];
+    double ym = wsum(s) / (double)k;
+    double tm = 0.5 * (double)(k - 1);
+    double sxx = 0.0, syy = 0.0, sxy = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        double dt = (double)i - tm, dy = y[i] - ym;
+        sxx = fma(dt, dt, sxx);
+        syy = fma(dy, dy, syy);
+        sxy = fma(dt, dy, sxy);
+    }
+    sxx = wsum(sxx) / (double)k;
+    syy = wsum(syy) / (double)k;
+    sxy = wsum(sxy) / (double)k;
+    return m_linregress((double)k, tm, ym, sxx, syy, sxy);
+}
+
+// leading decimal digit of |v| (shortest-repr digit == true digit for float32-origin values; 0 -> 0)
+__device__ __forceinline__ int leading_digit(float f, const double* dec) {
+    float a = fabsf(f);
+    if (a == 0.f) return 0;
+    double v = (double)a;
+    int e = ilogb(v);
+    int k = (int)floor((double)e * 0.30102999566398120);
+    if (k < TSFX_DEC_MIN) k = TSFX_DEC_MIN;
+    if (k + 1 <= TSFX_DEC_MAX && v >= dec[(k + 1 - TSFX_DEC_MIN) * 9]) ++k;
+    if (k > TSFX_DEC_MIN && v < dec[(k - TSFX_DEC_MIN) * 9]) --k;
+    const double* row = dec + (k - TSFX_DEC_MIN) * 9;
+    int d = 1;
+#pragma unroll
+    for (int j = 1; j < 9; ++j) d += (v >= row[j]);
+    return d;
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_basic(BasicArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    double* xc = reinterpret_cast<double*>(base);
+    double* scr = xc + A.npad;
+    double* lagS = scr + A.nscr;
+    float* xs = reinterpret_cast<float*>(lagS + A.nlag);
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+        const int n = load_series(A.R, s, xs, lane);
+        const Moments M = moments(xs, n, xc, lane);
+        const Extra E = extra_pass(xs, xc, n, M, lane);
+        double* orow = A.out + (size_t)s * A.ncols;
+        const double dn = (double)n;
+
+        if (A.lag_needed > 0) {         // lag products 0..min(lag_needed, n-1)
+            int kmax = min(A.lag_needed, n - 1);
+            for (int k = 0; k <= kmax; ++k) {
+                double v = lag_product(xc, n, k, lane);
+                if (lane == 0) lagS[k] = v;
+            }
+            __syncwarp();
+        }
+        // caches for multi-column calculators
+        int lt_key = -1; LinReg lt_fit;
+        bool lin_done = false; LinReg lin_fit;
+        bool pacf_done = false;
+
+        for (int j = 0; j < A.nd; ++j) {
+            const Desc d = A.descs[j];
+            double r = dnan();
+            switch (d.calc) {
+                case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: r = (M.var > sqrt(M.var)) ? 1.0 : 0.0; break;
+                case TSFX_LARGE_STANDARD_DEVIATION: r = (M.sd > d.p0 * (M.vmax - M.vmin)) ? 1.0 : 0.0; break;
+                case TSFX_HAS_DUPLICATE_MAX: r = E.cnt_max >= 2 ? 1.0 : 0.0; break;
+                case TSFX_HAS_DUPLICATE_MIN: r = E.cnt_min >= 2 ? 1.0 : 0.0; break;
+                case TSFX_SUM_VALUES: r = M.sum; break;
+                case TSFX_ABS_ENERGY: r = M.sumsq; break;
+                case TSFX_MEAN: r = M.mean; break;
+                case TSFX_LENGTH: r = dn; break;
+                case TSFX_STANDARD_DEVIATION: r = M.sd; break;
+                case TSFX_VARIANCE: r = M.var; break;
+                case TSFX_VARIATION_COEFFICIENT: r = (M.mean != 0.0) ? M.sd / M.mean : dnan(); break;
+                case TSFX_ROOT_MEAN_SQUARE: r = sqrt(M.sumsq / dn); break;
+                case TSFX_MAXIMUM: r = M.vmax; break;
+                case TSFX_MINIMUM: r = M.vmin; break;
+                case TSFX_ABSOLUTE_MAXIMUM: r = fmax(fabs(M.vmin), fabs(M.vmax)); break;
+                case TSFX_MEAN_ABS_CHANGE: r = E.sad / (double)(n - 1); break;
+                case TSFX_ABSOLUTE_SUM_OF_CHANGES: r = E.sad; break;
+                case TSFX_MEAN_CHANGE:
+                    r = n > 1 ? ((double)xs[n - 1] - (double)xs[0]) / (double)(n - 1) : dnan();
+                    break;
+                case TSFX_MEAN_SECOND_DERIVATIVE_CENTRAL:
+                    r = n > 2 ? ((double)xs[n - 1] - (double)xs[n - 2] - (double)xs[1] + (double)xs[0]) /
+                                    (2.0 * (double)(n - 2))
+                              : dnan();
+                    break;
+                case TSFX_SKEWNESS: {   // pandas nanops.nanskew
+                    double amax = fmax(fabs(M.vmin), fabs(M.vmax));
+                    double e1 = 2.220446049250313e-16 * amax;
+                    double m2 = M.m2, m3 = E.m3;
+                    if (fabs(m2) < e1 * e1 * dn) m2 = 0.0;
+                    if (fabs(m3) < e1 * e1 * e1 * dn) m3 = 0.0;
+                    if (n < 3) r = dnan();
+                    else if (m2 == 0.0) r = 0.0;
+                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2)));
+                    break;
+                }
+                case TSFX_KURTOSIS: {   // pandas nanops.nankurt
+                    double amax = fmax(fabs(M.vmin), fabs(M.vmax));
+                    double e1 = 2.220446049250313e-16 * amax, e2 = e1 * e1;
+                    double m2 = M.m2, m4 = E.m4;
+                    if (fabs(m2) < e2 * dn) m2 = 0.0;
+                    if (fabs(m4) < e2 * e2 * dn) m4 = 0.0;
+                    if (n < 4) r = dnan();
+                    else {
+                        double adj = 3.0 * (dn - 1.0) * (dn - 1.0) / ((dn - 2.0) * (dn - 3.0));
+                        double num = dn * (dn + 1.0) * (dn - 1.0) * m4;
+                        double den = (dn - 2.0) * (dn - 3.0) * m2 * m2;
+                        r = (den == 0.0) ? 0.0 : num / den - adj;
+                    }
+                    break;
+                }
+                case TSFX_LONGEST_STRIKE_BELOW_MEAN: r = (double)E.strike_below; break;
+                case TSFX_LONGEST_STRIKE_ABOVE_MEAN: r = (double)E.strike_above; break;
+                case TSFX_COUNT_ABOVE_MEAN: r = (double)E.cnt_above; break;
+                case TSFX_COUNT_BELOW_MEAN: r = (double)E.cnt_below; break;
+                case TSFX_LAST_LOCATION_OF_MAXIMUM: r = 1.0 - (double)(n - 1 - E.last_max) / dn; break;
+                case TSFX_FIRST_LOCATION_OF_MAXIMUM: r = (double)E.first_max / dn; break;
+                case TSFX_LAST_LOCATION_OF_MINIMUM: r = 1.0 - (double)(n - 1 - E.last_min) / dn; break;
+                case TSFX_FIRST_LOCATION_OF_MINIMUM: r = (double)E.first_min / dn; break;
+                case TSFX_CID_CE:
+                    if (d.i0) r = (M.sd != 0.0) ? sqrt(E.ssd) / M.sd : 0.0;
+                    else r = sqrt(E.ssd);
+                    break;
+                case TSFX_RATIO_BEYOND_R_SIGMA: {
+                    double thr = d.p0 * M.sd;
+                    int c = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && fabs(xc[i]) > thr); }
+                    r = (double)c / dn;
+                    break;
+                }
+                case TSFX_VALUE_COUNT: {
+                    int c = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && (double)xs[i] == d.p0); }
+                    r = (double)c;
+                    break;
+                }
+                case TSFX_RANGE_COUNT: {
+                    int c = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        int i = b0 + lane;
+                        double v = i < n ? (double)xs[i] : 0.0;
+                        c += wcount(i < n && v >= d.p0 && v < d.p1);
+                    }
+                    r = (double)c;
+                    break;
+                }
+                case TSFX_COUNT_ABOVE: {
+                    int c = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && (double)xs[i] >= d.p0); }
+                    r = (double)c / dn;
+                    break;
+                }
+                case TSFX_COUNT_BELOW: {
+                    int c = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && (double)xs[i] <= d.p0); }
+                    r = (double)c / dn;
+                    break;
+                }
+                case TSFX_NUMBER_CROSSING_M: {
+                    int c = 0;
+                    for (int b0 = 0; b0 + 1 < n; b0 += 32) {
+                        int i = b0 + lane;
+                        bool p = false;
+                        if (i + 1 < n) p = ((double)xs[i] > d.p0) != ((double)xs[i + 1] > d.p0);
+                        c += wcount(p);
+                    }
+                    r = (double)c;
+                    break;
+                }
+                case TSFX_NUMBER_PEAKS: {
+                    int sup = d.i0, c = 0;
+                    for (int b0 = sup; b0 < n - sup; b0 += 32) {
+                        int i = b0 + lane;
+                        bool p = i < n - sup;
+                        if (p) {
+                            float v = xs[i];
+                            for (int q = 1; q <= sup; ++q)
+                                if (!(v > xs[i - q] && v > xs[i + q])) { p = false; break; }
+                        }
+                        c += wcount(p);
+                    }
+                    r = (double)c;
+                    break;
+                }
+                case TSFX_AUTOCORRELATION: {
+                    int lag = d.i0;
+                    if (n < lag || M.var <= 1e-8) r = dnan();      // np.isclose(v, 0) with v >= 0
+                    else if (lag >= n) r = dnan();                  // 0 / 0
+                    else r = lagS[lag] / ((double)(n - lag) * M.var);
+                    break;
+                }
+                case TSFX_AGG_AUTOCORRELATION: {
+                    int cnt;
+                    bool zero = (fabs(M.var) < 1e-10) || n == 1;
+                    cnt = zero ? min(d.i0, n) : min(d.i0, n - 1);
+                    if (cnt <= 0) { r = dnan(); break; }
+                    if (zero) { r = 0.0; break; }
+                    // a[k-1] = (S[k]/(n-k)) / (S[0]/n), k = 1..cnt ; staged in scr
+                    double a0 = lagS[0] / dn;
+                    for (int k = 1 + lane; k <= cnt; k += 32) scr[k - 1] = (lagS[k] / (double)(n - k)) / a0;
+                    __syncwarp();
+                    if (d.attr == TSFX_AGG_MEDIAN) {
+                        int k1 = (cnt - 1) / 2, k2 = cnt / 2;
+                        double v1 = 0.0, v2 = 0.0;
+                        for (int i = lane; i < cnt; i += 32) {
+                            double xi = scr[i];
+                            int rk = 0;
+                            for (int q = 0; q < cnt; ++q) { double xq = scr[q]; rk += (xq < xi) || (xq == xi && q < i); }
+                            if (rk == k1) v1 = xi;
+                            if (rk == k2) v2 = xi;
+                        }
+                        r = 0.5 * (wsum(v1) + wsum(v2));
+                    } else {
+                        double s1 = 0.0;
+                        for (int i = lane; i < cnt; i += 32) s1 += scr[i];
+                        double mu = wsum(s1) / (double)cnt;
+                        if (d.attr == TSFX_AGG_MEAN) r = mu;
+                        else {
+                            double q2 = 0.0;
+                            for (int i = lane; i < cnt; i += 32) { double dd = scr[i] - mu; q2 = fma(dd, dd, q2); }
+                            double v = wsum(q2) / (double)cnt;
+                            r = d.attr == TSFX_AGG_STD ? sqrt(v) : v;
+                        }
+                    }
+                    __syncwarp();
+                    break;
+                }
+                case TSFX_PARTIAL_AUTOCORRELATION: {
+                    // pacf staged at lagS[nlag_pacf_off ..]; computed once per series by lane 0
+                    double* pac = lagS + A.pacf_off;
+                    int want = d.i1;
+                    if (!pacf_done) {
+                        if (lane == 0) {
+                            int use = (want >= n / 2) ? n / 2 - 1 : want;
+                            if (n <= 1 || use <= 0) { for (int k = 0; k <= want; ++k) pac[k] = dnan(); }
+                            else {
+                                double* acv = pac + (want + 1);
+                                double* work = acv + (want + 1);
+                                acv[0] = lagS[0] / dn;
+                                for (int k = 1; k <= use; ++k) acv[k] = lagS[k] / (double)(n - k);
+                                m_levinson_pacf(acv, use, pac, work);
+                                for (int k = use + 1; k <= want; ++k) pac[k] = dnan();
+                            }
+                        }
+                        __syncwarp();
+                        pacf_done = true;
+                    }
+                    r = pac[d.i0];
+                    break;
+                }
+                case TSFX_TIME_REVERSAL_ASYMMETRY_STATISTIC: {
+                    int l = d.i0;
+                    if (2 * l >= n) { r = 0.0; break; }
+                    double a = 0.0;
+                    for (int i = lane; i < n - 2 * l; i += 32) {
+                        double x0 = xs[i], x1 = xs[i + l], x2 = xs[i + 2 * l];
+                        a += x2 * x2 * x1 - x1 * x0 * x0;
+                    }
+                    r = wsum(a) / (double)(n - 2 * l);
+                    break;
+                }
+                case TSFX_C3: {
+                    int l = d.i0;
+                    if (2 * l >= n) { r = 0.0; break; }
+                    double a = 0.0;
+                    for (int i = lane; i < n - 2 * l; i += 32) a += (double)xs[i + 2 * l] * (double)xs[i + l] * (double)xs[i];
+                    r = wsum(a) / (double)(n - 2 * l);
+                    break;
+                }
+                case TSFX_INDEX_MASS_QUANTILE: {
+                    double tot = 0.0;
+                    for (int i = lane; i < n; i += 32) tot += fabs((double)xs[i]);
+                    tot = wsum(tot);
+                    if (tot == 0.0) { r = dnan(); break; }
+                    double carry = 0.0;
+                    int found = -1;
+                    for (int b0 = 0; b0 < n && found < 0; b0 += 32) {
+                        int i = b0 + lane;
+                        double v = i < n ? fabs((double)xs[i]) : 0.0;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {          // inclusive scan
+                            double t = __shfl_up_sync(FULL, v, o);
+                            if (lane >= o) v += t;
+                        }
+                        double cum = carry + v;
+                        unsigned hit = __ballot_sync(FULL, i < n && __ddiv_rn(cum, tot) >= d.p0);
+                        if (hit) found = b0 + __ffs(hit) - 1;
+                        carry = __shfl_sync(FULL, cum, 31);
+                    }
+                    if (found < 0) found = 0;                       // np.argmax of all-False is 0
+                    r = (double)(found + 1) / dn;
+                    break;
+                }
+                case TSFX_ENERGY_RATIO_BY_CHUNKS: {
+                    if (M.sumsq == 0.0) { r = dnan(); break; }
+                    int ns = d.i0, fo = d.i1;
+                    int q = n / ns, rem = n % ns;
+                    int lo = fo * q + min(fo, rem), hi = lo + q + (fo < rem ? 1 : 0);
+                    double a = 0.0;
+                    for (int i = lo + lane; i < hi; i += 32) { double v = xs[i]; a = fma(v, v, a); }
+                    r = wsum(a) / M.sumsq;
+                    break;
+                }
+                case TSFX_BINNED_ENTROPY: {
+                    r = binned_entropy_of([&](int i) { return (double)xs[i]; }, n, M.vmin, M.vmax, d.i0,
+                                          reinterpret_cast<int*>(scr), lane);
+                    break;
+                }
+                case TSFX_LINEAR_TREND: {
+                    if (!lin_done) {
+                        double tm = 0.5 * (double)(n - 1);
+                        double sxx = 0.0, sxy = 0.0;
+                        for (int i = lane; i < n; i += 32) {
+                            double dt = (double)i - tm;
+                            sxx = fma(dt, dt, sxx);
+                            sxy = fma(dt, xc[i], sxy);
+                        }
+                        sxx = wsum(sxx) / dn;
+                        sxy = wsum(sxy) / dn;
+                        lin_fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
+                        lin_done = true;
+                    }
+                    r = m_linreg_pick(lin_fit, d.attr);
+                    break;
+                }
+                case TSFX_AGG_LINEAR_TREND: {
+                    int cl = d.i0;
+                    if (cl >= n) { r = dnan(); break; }
+                    int key = (cl << 4) | d.i1;
+                    if (key != lt_key) {
+                        int k = (n + cl - 1) / cl;
+                        for (int c = lane; c < k; c += 32) scr[c] = agg_chunk(xs, c * cl, min(n, (c + 1) * cl), d.i1);
+                        __syncwarp();
+                        lt_fit = linreg_index(scr, k, lane);
+                        __syncwarp();
+                        lt_key = key;
+                    }
+                    r = m_linreg_pick(lt_fit, d.attr);
+                    break;
+                }
+                case TSFX_BENFORD_CORRELATION: {
+                    int cnt[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) cnt[q] = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        int i = b0 + lane;
+                        int dg = i < n ? leading_digit(xs[i], A.dec) : -1;
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) cnt[q] += wcount(dg == q + 1);
+                    }
+                    // np.corrcoef(benford, observed)[0, 1]
+                    double ben[9], obs[9], mb = 0.0, mo = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { ben[q] = log10(1.0 + 1.0 / (double)(q + 1)); obs[q] = (double)cnt[q] / dn; mb += ben[q]; mo += obs[q]; }
+                    mb /= 9.0; mo /= 9.0;
+                    double sbb = 0.0, soo = 0.0, sbo = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { double a = ben[q] - mb, b = obs[q] - mo; sbb += a * a; soo += b * b; sbo += a * b; }
+                    r = sbo / sqrt(sbb) / sqrt(soo);
+                    if (r > 1.0) r = 1.0;
+                    if (r < -1.0) r = -1.0;
+                    break;
+                }
+                case TSFX_QUERY_SIMILARITY_COUNT:
+                case TSFX_CONST_NAN:
+                default: r = dnan(); break;
+            }
+            if (lane == 0) orow[d.col] = r;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ launcher
+cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int sm_count) {
+    BasicArgs A = A0;
+    A.npad = (max_len + 3) & ~3;
+    size_t per = (size_t)A.npad * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + (size_t)A.npad * 4;
+    per = (per + 15) & ~(size_t)15;
+    A.bytes_per_warp = (int)per;
+    int wpc = (int)(100 * 1024 / per);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 8) wpc = 8;
+    if (per * wpc > 227 * 1024) return cudaErrorInvalidConfiguration;
+    size_t smem = per * wpc;
+    int64_t ctas = (A.R.n_series + wpc - 1) / wpc;
+    int64_t cap = (int64_t)sm_count * 16;
+    int grid = (int)(ctas < cap ? ctas : cap);
+    if (grid < 1) grid = 1;
+#define TSFX_LAUNCH_BASIC(W)                                                                              \
+    {                                                                                                     \
+        cudaError_t e = cudaFuncSetAttribute(k_basic<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                   \
+        k_basic<W><<<grid, W * 32, smem, st>>>(A);                                                        \
+    }
+    switch (wpc) {
+        case 8: TSFX_LAUNCH_BASIC(8) break;
+        case 7: case 6: case 5: case 4: wpc = 4; smem = per * 4; grid = (int)std::min<int64_t>((A.R.n_series + 3) / 4, cap); TSFX_LAUNCH_BASIC(4) break;
+        case 3: case 2: wpc = 2; smem = per * 2; grid = (int)std::min<int64_t>((A.R.n_series + 1) / 2, cap); TSFX_LAUNCH_BASIC(2) break;
+        default: wpc = 1; smem = per; grid = (int)std::min<int64_t>(A.R.n_series, cap); TSFX_LAUNCH_BASIC(1) break;
+    }
+#undef TSFX_LAUNCH_BASIC
+    return cudaGetLastError();
+}
+
+}  // namespace tsfx

@@ -1,0 +1,547 @@
+// tsfx_api.cu -- the C ABI of libtsfx.so (include/tsfx.h): context, plan, extraction entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tsfx_common.cuh"
+#include "tsfx_kernels.h"
+#include "tsfx_csr.h"
+
+using namespace tsfx;
+
+static std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+static const char* kGroupNames[G_COUNT] = {"basic", "sorted", "spectral", "la", "entropy", "seq"};
+
+struct tsfx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    DevBuf values, begin, len, out, misc;
+    double* d_dec = nullptr;
+    double2* d_tw = nullptr;
+    int tw_n = 0;
+    cudaEvent_t ev[G_COUNT][2];
+    bool ev_used[G_COUNT];
+    float ms[G_COUNT];
+    int launches = 0;
+    CsrWorkspace csr;
+};
+
+struct tsfx_plan {
+    tsfx_ctx* ctx = nullptr;
+    std::vector<Desc> host[G_COUNT];
+    Desc* dev[G_COUNT] = {nullptr};
+    int ncols = 0;
+    int lag_needed = 0, pacf_want = -1;
+    int basic_bins = 0, fourier_bins = 0;
+    int need_fft = 0, need_welch = 0;
+    int max_ar_k = 0, need_adf = 0;
+    int max_lz_bins = 0, max_perm_dim = 0, max_cwt_peaks_n = 0;
+    int friedrich_r = 0;
+    double* d_tables = nullptr;
+    int64_t* d_toff = nullptr;
+    int32_t* d_thalf = nullptr;
+    int n_tables = 0;
+    std::vector<int64_t> toff;
+    std::vector<int32_t> thalf;
+};
+
+static int fail(tsfx_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(ctx, TSFX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));  \
+    } while (0)
+
+static int group_of(int calc) {
+    switch (calc) {
+        case TSFX_SYMMETRY_LOOKING: case TSFX_HAS_DUPLICATE: case TSFX_MEDIAN:
+        case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
+        case TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS:
+        case TSFX_SUM_OF_REOCCURRING_VALUES: case TSFX_SUM_OF_REOCCURRING_DATA_POINTS:
+        case TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH: case TSFX_QUANTILE:
+        case TSFX_MEAN_N_ABSOLUTE_MAX: case TSFX_CHANGE_QUANTILES: case TSFX_FRIEDRICH_COEFFICIENTS:
+        case TSFX_MAX_LANGEVIN_FIXED_POINT:
+            return G_SORTED;
+        case TSFX_FFT_COEFFICIENT: case TSFX_FFT_AGGREGATED: case TSFX_SPKT_WELCH_DENSITY:
+        case TSFX_FOURIER_ENTROPY: case TSFX_CWT_COEFFICIENTS:
+            return G_SPECTRAL;
+        case TSFX_AR_COEFFICIENT: case TSFX_AUGMENTED_DICKEY_FULLER:
+            return G_LA;
+        case TSFX_SAMPLE_ENTROPY: case TSFX_APPROXIMATE_ENTROPY:
+            return G_ENTROPY;
+        case TSFX_LEMPEL_ZIV_COMPLEXITY: case TSFX_PERMUTATION_ENTROPY: case TSFX_NUMBER_CWT_PEAKS:
+            return G_SEQ;
+        default:
+            return G_BASIC;
+    }
+}
+
+extern "C" int tsfx_version(void) { return TSFX_VERSION; }
+
+extern "C" const char* tsfx_last_error(const tsfx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
+    if (!out) return fail(nullptr, TSFX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    tsfx_ctx* ctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TSFX_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, TSFX_E_INVALID, "device index out of range");
+    ctx = new (std::nothrow) tsfx_ctx();
+    if (!ctx) return fail(nullptr, TSFX_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    for (int g = 0; g < G_COUNT; ++g) { ctx->ev_used[g] = false; ctx->ms[g] = 0.f; ctx->ev[g][0] = ctx->ev[g][1] = nullptr; }
+#define CKC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            std::string m = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+            delete ctx;                                                                               \
+            return fail(nullptr, TSFX_E_CUDA, m);                                                     \
+        }                                                                                             \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    for (int g = 0; g < G_COUNT; ++g) { CKC(cudaEventCreate(&ctx->ev[g][0])); CKC(cudaEventCreate(&ctx->ev[g][1])); }
+    // decimal threshold table d * 10^k (correctly rounded literals via strtod)
+    {
+        std::vector<double> dec((TSFX_DEC_MAX - TSFX_DEC_MIN + 1) * 9);
+        for (int k = TSFX_DEC_MIN; k <= TSFX_DEC_MAX; ++k)
+            for (int d = 1; d <= 9; ++d) {
+                char buf[32];
+                snprintf(buf, sizeof buf, "%de%d", d, k);
+                dec[(k - TSFX_DEC_MIN) * 9 + (d - 1)] = strtod(buf, nullptr);
+            }
+        CKC(cudaMalloc(&ctx->d_dec, dec.size() * sizeof(double)));
+        CKC(cudaMemcpy(ctx->d_dec, dec.data(), dec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+#undef CKC
+    *out = ctx;
+    return TSFX_OK;
+}
+
+extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release();
+    ctx->csr.release();
+    if (ctx->d_dec) cudaFree(ctx->d_dec);
+    if (ctx->d_tw) cudaFree(ctx->d_tw);
+    for (int g = 0; g < G_COUNT; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int tsfx_sync(tsfx_ctx* ctx) {
+    if (!ctx) return TSFX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ plan
+extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, int32_t n_descs, int32_t n_cols,
+                                const double* tables, const int64_t* table_off, const int32_t* table_half,
+                                int32_t n_tables, tsfx_plan** out) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (!out || (!descs && n_descs > 0) || n_descs < 0 || n_cols < 0)
+        return fail(ctx, TSFX_E_INVALID, "tsfx_plan_create: bad arguments");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    tsfx_plan* P = new (std::nothrow) tsfx_plan();
+    if (!P) return fail(ctx, TSFX_E_NOMEM, "out of host memory");
+    P->ctx = ctx;
+    P->ncols = n_cols;
+    for (int i = 0; i < n_descs; ++i) {
+        const Desc& d = descs[i];
+        if (d.calc < 0 || d.calc >= TSFX_N_CALCS || d.col < 0 || d.col >= n_cols) {
+            delete P;
+            return fail(ctx, TSFX_E_INVALID, "tsfx_plan_create: descriptor " + std::to_string(i) + " out of range");
+        }
+        P->host[group_of(d.calc)].push_back(d);
+        switch (d.calc) {
+            case TSFX_AUTOCORRELATION: P->lag_needed = std::max(P->lag_needed, d.i0); break;
+            case TSFX_AGG_AUTOCORRELATION: P->lag_needed = std::max(P->lag_needed, d.i0); break;
+            case TSFX_PARTIAL_AUTOCORRELATION:
+                P->lag_needed = std::max(P->lag_needed, d.i1);
+                P->pacf_want = std::max(P->pacf_want, d.i1);
+                break;
+            case TSFX_BINNED_ENTROPY: P->basic_bins = std::max(P->basic_bins, d.i0); break;
+            case TSFX_FOURIER_ENTROPY: P->fourier_bins = std::max(P->fourier_bins, d.i0); P->need_welch = 1; break;
+            case TSFX_SPKT_WELCH_DENSITY: P->need_welch = 1; break;
+            case TSFX_FFT_COEFFICIENT: case TSFX_FFT_AGGREGATED: P->need_fft = 1; break;
+            case TSFX_CWT_COEFFICIENTS:
+                if (d.i1 < 0 || d.i1 >= n_tables) { delete P; return fail(ctx, TSFX_E_INVALID, "cwt table index out of range"); }
+                break;
+            case TSFX_AR_COEFFICIENT:
+                if (d.i1 < 1 || d.i1 > 32) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "ar_coefficient: k must be in 1..32"); }
+                P->max_ar_k = std::max(P->max_ar_k, d.i1);
+                break;
+            case TSFX_AUGMENTED_DICKEY_FULLER: P->need_adf = 1; break;
+            case TSFX_APPROXIMATE_ENTROPY:
+                if (d.i0 != 2) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "approximate_entropy: only m=2"); }
+                break;
+            case TSFX_LEMPEL_ZIV_COMPLEXITY: P->max_lz_bins = std::max(P->max_lz_bins, d.i0); break;
+            case TSFX_PERMUTATION_ENTROPY:
+                if (d.i1 < 2 || d.i1 > 8 || d.i0 < 1) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "permutation_entropy: dimension 2..8, tau >= 1"); }
+                P->max_perm_dim = std::max(P->max_perm_dim, d.i1);
+                break;
+            case TSFX_NUMBER_CWT_PEAKS:
+                if (d.i0 < 1 || d.i0 > 16) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "number_cwt_peaks: n must be in 1..16"); }
+                P->max_cwt_peaks_n = std::max(P->max_cwt_peaks_n, d.i0);
+                break;
+            case TSFX_FRIEDRICH_COEFFICIENTS: case TSFX_MAX_LANGEVIN_FIXED_POINT:
+                if (d.i1 != 3 || d.i2 < 1 || d.i2 > 256) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "friedrich: only m=3, r in 1..256"); }
+                P->friedrich_r = std::max(P->friedrich_r, d.i2);
+                break;
+            default: break;
+        }
+    }
+    if (P->lag_needed > 4096) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "lag > 4096"); }
+    for (int g = 0; g < G_COUNT; ++g) {
+        std::stable_sort(P->host[g].begin(), P->host[g].end(), [](const Desc& a, const Desc& b) {
+            if (a.calc != b.calc) return a.calc < b.calc;
+            if (a.i1 != b.i1) return a.i1 < b.i1;
+            if (a.i2 != b.i2) return a.i2 < b.i2;
+            if (a.p0 != b.p0) return a.p0 < b.p0;
+            if (a.p1 != b.p1) return a.p1 < b.p1;
+            if (a.i0 != b.i0) return a.i0 < b.i0;
+            return a.col < b.col;
+        });
+        if (!P->host[g].empty()) {
+            size_t bytes = P->host[g].size() * sizeof(Desc);
+            cudaError_t e = cudaMalloc(&P->dev[g], bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(P->dev[g], P->host[g].data(), bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_CUDA, cudaGetErrorString(e)); }
+        }
+    }
+    if (n_tables > 0) {
+        if (!tables || !table_off || !table_half) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_INVALID, "cwt tables missing"); }
+        P->n_tables = n_tables;
+        P->toff.assign(table_off, table_off + n_tables + 1);
+        P->thalf.assign(table_half, table_half + n_tables);
+        size_t tb = (size_t)table_off[n_tables] * sizeof(double);
+        cudaError_t e = cudaMalloc(&P->d_tables, std::max<size_t>(tb, 8));
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_tables, tables, tb, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&P->d_toff, (n_tables + 1) * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_toff, table_off, (n_tables + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&P->d_thalf, n_tables * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_thalf, table_half, n_tables * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = P;
+    return TSFX_OK;
+}
+
+extern "C" void tsfx_plan_destroy(tsfx_plan* P) {
+    if (!P) return;
+    if (P->ctx) cudaSetDevice(P->ctx->device);
+    for (int g = 0; g < G_COUNT; ++g) if (P->dev[g]) cudaFree(P->dev[g]);
+    if (P->d_tables) cudaFree(P->d_tables);
+    if (P->d_toff) cudaFree(P->d_toff);
+    if (P->d_thalf) cudaFree(P->d_thalf);
+    delete P;
+}
+
+// ------------------------------------------------------------------------------------------ launch all groups
+static int even(int v) { return (v + 1) & ~1; }
+
+static int ensure_twiddle(tsfx_ctx* ctx, int n_pow2) {
+    if (n_pow2 <= ctx->tw_n) return TSFX_OK;
+    if (ctx->d_tw) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_tw); ctx->d_tw = nullptr; ctx->tw_n = 0; }
+    CK(cudaMalloc(&ctx->d_tw, (size_t)(n_pow2 / 2 + 1) * sizeof(double2)));
+    CK(launch_fill_twiddle(ctx->d_tw, n_pow2, ctx->stream));
+    ctx->tw_n = n_pow2;
+    return TSFX_OK;
+}
+
+static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int max_len, double* d_out, uint32_t flags) {
+    const bool timing = (flags & TSFX_FLAG_TIMING) != 0;
+    for (int g = 0; g < G_COUNT; ++g) ctx->ev_used[g] = false;
+    ctx->launches = 0;
+    if (R.n_series == 0) return TSFX_OK;
+    if (max_len < 1) return fail(ctx, TSFX_E_INVALID, "series of length < 1");
+    auto too_long = [&](const char* g) {
+        return fail(ctx, TSFX_E_TOO_LONG, std::string("series length ") + std::to_string(max_len) +
+                                              " exceeds the shared-memory staging of kernel group " + g);
+    };
+    for (int g = 0; g < G_COUNT; ++g) {
+        if (P->host[g].empty()) continue;
+        if (timing) { CK(cudaEventRecord(ctx->ev[g][0], ctx->stream)); }
+        cudaError_t e = cudaSuccess;
+        switch (g) {
+            case G_BASIC: {
+                BasicArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.lag_needed = P->lag_needed;
+                int pac = P->pacf_want >= 0 ? 4 * (P->pacf_want + 1) : 0;
+                A.pacf_off = P->lag_needed + 1;
+                A.nlag = even(P->lag_needed + 1 + pac);
+                A.nscr = even(std::max(std::max(max_len, 64), (P->basic_bins + 1) / 2));
+                A.dec = ctx->d_dec;
+                e = launch_basic(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_SORTED: {
+                SortedArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.nscr = even(4 * (P->friedrich_r + 2) + 16);
+                e = launch_sorted(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_SPECTRAL: {
+                SpectralArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                int p2 = 1;
+                while (p2 < max_len) p2 <<= 1;
+                if (p2 > max_len) p2 >>= 1;            // largest power of two <= max_len
+                p2 = std::max(p2, 256);
+                int rc = ensure_twiddle(ctx, p2);
+                if (rc) return rc;
+                A.twiddle = ctx->d_tw; A.tw_n = ctx->tw_n;
+                A.tables = P->d_tables; A.table_off = P->d_toff; A.table_half = P->d_thalf;
+                A.need_fft = P->need_fft; A.need_welch = P->need_welch;
+                A.max_hist = P->fourier_bins;
+                e = launch_spectral(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_LA: {
+                LaArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                e = launch_la(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_ENTROPY: {
+                EntropyArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                e = launch_entropy(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_SEQ: {
+                SeqArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                e = launch_seq(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+        }
+        if (e == cudaErrorInvalidConfiguration) return too_long(kGroupNames[g]);
+        if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("launch ") + kGroupNames[g] + ": " + cudaGetErrorString(e));
+        ctx->launches += 1;
+        if (timing) { CK(cudaEventRecord(ctx->ev[g][1], ctx->stream)); ctx->ev_used[g] = true; }
+    }
+    return TSFX_OK;
+}
+
+static int check_args(tsfx_ctx* ctx, const tsfx_plan* plan, const void* values, const void* out, int64_t n_series) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
+    if (n_series < 0) return fail(ctx, TSFX_E_INVALID, "n_series < 0");
+    if (n_series > 0 && (!values || !out)) return fail(ctx, TSFX_E_INVALID, "NULL values/out");
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_values,
+                                const int64_t* begin, const int32_t* len, int64_t n_series, double* out,
+                                uint32_t flags) {
+    int rc = check_args(ctx, plan, values, out, n_series);
+    if (rc) return rc;
+    if (n_series == 0) return TSFX_OK;
+    if (!begin || !len) return fail(ctx, TSFX_E_INVALID, "NULL begin/len");
+    CK(cudaSetDevice(ctx->device));
+    SeriesRef R;
+    R.dense_len = 0;
+    R.n_series = n_series;
+    int max_len = 0;
+    if (flags & TSFX_FLAG_DEVICE_PTRS) {
+        R.values = values; R.begin = begin; R.len = len;
+        int rc2 = csr_max_len(ctx->csr, len, n_series, ctx->stream, &max_len);
+        if (rc2) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
+        return run_groups(ctx, plan, R, max_len, out, flags);
+    }
+    for (int64_t s = 0; s < n_series; ++s) {
+        if (len[s] < 1 || begin[s] < 0 || begin[s] + len[s] > n_values)
+            return fail(ctx, TSFX_E_INVALID, "series " + std::to_string(s) + " has an invalid (begin, len)");
+        max_len = std::max(max_len, (int)len[s]);
+    }
+    size_t ob = (size_t)n_series * plan->ncols * sizeof(double);
+    CK(ctx->values.reserve((size_t)n_values * sizeof(float) + 16));
+    CK(ctx->begin.reserve((size_t)n_series * sizeof(int64_t)));
+    CK(ctx->len.reserve((size_t)n_series * sizeof(int32_t)));
+    CK(ctx->out.reserve(std::max<size_t>(ob, 8)));
+    CK(cudaMemcpyAsync(ctx->values.p, values, (size_t)n_values * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->begin.p, begin, (size_t)n_series * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->len.p, len, (size_t)n_series * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    R.values = (const float*)ctx->values.p; R.begin = (const int64_t*)ctx->begin.p; R.len = (const int32_t*)ctx->len.p;
+    rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_series,
+                                  int32_t len, double* out, uint32_t flags) {
+    int rc = check_args(ctx, plan, values, out, n_series);
+    if (rc) return rc;
+    if (n_series == 0) return TSFX_OK;
+    if (len < 1) return fail(ctx, TSFX_E_INVALID, "len < 1");
+    CK(cudaSetDevice(ctx->device));
+    SeriesRef R;
+    R.begin = nullptr; R.len = nullptr; R.dense_len = len; R.n_series = n_series;
+    if (flags & TSFX_FLAG_DEVICE_PTRS) {
+        R.values = values;
+        return run_groups(ctx, plan, R, len, out, flags);
+    }
+    // host path: pipelined over row blocks so H2D, kernels and D2H of neighbouring blocks overlap
+    size_t ncols = (size_t)plan->ncols;
+    size_t vb = (size_t)n_series * len * sizeof(float), ob = (size_t)n_series * ncols * sizeof(double);
+    CK(ctx->values.reserve(vb + 16));
+    CK(ctx->out.reserve(std::max<size_t>(ob, 8)));
+    CK(cudaMemcpyAsync(ctx->values.p, values, vb, cudaMemcpyHostToDevice, ctx->stream));
+    R.values = (const float*)ctx->values.p;
+    rc = run_groups(ctx, plan, R, len, (double*)ctx->out.p, flags);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names_out, int32_t cap) {
+    if (!ctx) return TSFX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int k = 0;
+    for (int g = 0; g < G_COUNT && k < cap; ++g) {
+        if (!ctx->ev_used[g]) continue;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[g][0], ctx->ev[g][1]));
+        if (ms_out) ms_out[k] = ms;
+        if (names_out) names_out[k] = kGroupNames[g];
+        ++k;
+    }
+    return k;
+}
+
+extern "C" int tsfx_last_launch_count(const tsfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ stage (a)
+extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sort_keys, int32_t sort_key_is_f64,
+                              const float* values, int64_t n_rows, int64_t* out_ids, int64_t* out_begin,
+                              int32_t* out_len, float* sorted_values, int64_t out_capacity, int64_t* n_series_out) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (n_rows < 0 || !n_series_out || (n_rows > 0 && (!ids || !values)))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_build_csr: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    *n_series_out = 0;
+    if (n_rows == 0) return TSFX_OK;
+    std::string msg;
+    int64_t ns = 0;
+    int rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    *n_series_out = ns;
+    if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
+    if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_begin) CK(cudaMemcpyAsync(out_begin, ctx->csr.d_begin, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_len) CK(cudaMemcpyAsync(out_len, ctx->csr.d_len, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sorted_values) CK(cudaMemcpyAsync(sorted_values, ctx->csr.d_values, n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
+                                 int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t* out_ids,
+                                 double* out, int64_t out_capacity, int64_t* n_series_out, uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
+    if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long takes host pointers");
+    if (n_rows < 0 || !n_series_out || (n_rows > 0 && (!ids || !values || !out)))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    *n_series_out = 0;
+    if (n_rows == 0) return TSFX_OK;
+    std::string msg;
+    int64_t ns = 0;
+    int rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    *n_series_out = ns;
+    if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
+    int max_len = 0;
+    if (csr_max_len(ctx->csr, ctx->csr.d_len, ns, ctx->stream, &max_len)) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
+    size_t ob = (size_t)ns * plan->ncols * sizeof(double);
+    CK(ctx->out.reserve(std::max<size_t>(ob, 8)));
+    SeriesRef R;
+    R.values = ctx->csr.d_values; R.begin = ctx->csr.d_begin; R.len = ctx->csr.d_len; R.dense_len = 0; R.n_series = ns;
+    rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
+    if (rc) return rc;
+    if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ roll_time_series views
+extern "C" int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, int64_t n_series,
+                                     int32_t rolling_direction, int32_t max_timeshift, int32_t min_timeshift,
+                                     int64_t* win_begin, int32_t* win_len, int64_t* win_parent,
+                                     int32_t* win_end_index, int64_t capacity) {
+    // dataframe_functions.py:340-373 with rolling_direction > 0: for a series of length L and every
+    // shift t in reversed(range(L, 0, -rolling_direction)) the window is rows [max(t-max_timeshift-1,0), t);
+    // it is kept when it has at least min_timeshift+1 rows; its id is (parent id, time of row t-1).
+    if (!begin || !len || n_series < 0 || rolling_direction <= 0 || max_timeshift < 0 || min_timeshift < 0)
+        return TSFX_E_INVALID;
+    int64_t k = 0;
+    for (int64_t s = 0; s < n_series; ++s) {
+        int32_t L = len[s];
+        if (L < 1) return TSFX_E_INVALID;
+        int32_t first = L - ((L - 1) / rolling_direction) * rolling_direction;   // smallest t of the range
+        for (int32_t t = first; t <= L; t += rolling_direction) {
+            int32_t lo = t - max_timeshift - 1;
+            if (lo < 0) lo = 0;
+            int32_t wl = t - lo;
+            if (wl < min_timeshift + 1) continue;
+            if (win_begin) {
+                if (k >= capacity) return TSFX_E_INVALID;
+                win_begin[k] = begin[s] + lo;
+                win_len[k] = wl;
+                if (win_parent) win_parent[k] = s;
+                if (win_end_index) win_end_index[k] = t - 1;
+            }
+            ++k;
+        }
+    }
+    return k;
+}

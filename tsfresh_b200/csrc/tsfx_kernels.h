@@ -1,0 +1,88 @@
+// tsfx_kernels.h -- argument blocks and launchers of the kernel groups (internal to libtsfx.so).
+#pragma once
+#include <cuda_runtime.h>
+#include "tsfx_common.cuh"
+
+#define TSFX_DEC_MIN (-46)
+#define TSFX_DEC_MAX 39
+
+namespace tsfx {
+
+enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_COUNT };
+
+struct BasicArgs {
+    SeriesRef R;
+    const Desc* descs;   // device, this group's descriptors
+    int nd;
+    double* out;
+    int ncols;
+    int npad, nscr, nlag, bytes_per_warp;   // shared-memory carve-up (doubles / doubles / doubles / bytes)
+    int lag_needed;      // largest lag product any descriptor reads (0 = none)
+    int pacf_off;        // offset (doubles) of the pacf staging area inside lagS
+    const double* dec;   // device table d*10^k, k = TSFX_DEC_MIN..TSFX_DEC_MAX, 9 per decade
+};
+cudaError_t launch_basic(const BasicArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+struct SortedArgs {
+    SeriesRef R;
+    const Desc* descs;
+    int nd;
+    double* out;
+    int ncols;
+    int npad, npow2, nscr, bytes_per_warp;
+};
+cudaError_t launch_sorted(const SortedArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+struct SpectralArgs {
+    SeriesRef R;
+    const Desc* descs;
+    int nd;
+    double* out;
+    int ncols;
+    int npad, nspec, bytes_per_warp;
+    const double2* twiddle;    // device: exp(-2 pi i k / tw_n), k = 0 .. tw_n/2
+    int tw_n;                  // power of two >= largest power-of-two FFT length in use
+    const double* tables;      // cwt tables (device)
+    const int64_t* table_off;
+    const int32_t* table_half;
+    int need_fft, need_welch;
+    int max_hist;
+};
+cudaError_t launch_spectral(const SpectralArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+struct LaArgs {
+    SeriesRef R;
+    const Desc* descs;
+    int nd;
+    double* out;
+    int ncols;
+    int npad, nscr, bytes_per_warp;
+};
+cudaError_t launch_la(const LaArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+struct EntropyArgs {
+    SeriesRef R;
+    const Desc* descs;
+    int nd;
+    double* out;
+    int ncols;
+    int npad, bytes_per_warp;
+};
+cudaError_t launch_entropy(const EntropyArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+struct SeqArgs {
+    SeriesRef R;
+    const Desc* descs;
+    int nd;
+    double* out;
+    int ncols;
+    int npad, nscr, bytes_per_warp;
+};
+cudaError_t launch_seq(const SeqArgs& A, int max_len, cudaStream_t st, int sm_count);
+
+// plain fill of a column set with NaN is done by BASIC (TSFX_CONST_NAN)
+
+// twiddle table fill: tw[k] = exp(-2 pi i k / n), k = 0..n/2
+cudaError_t launch_fill_twiddle(double2* tw, int n, cudaStream_t st);
+
+}  // namespace tsfx
