@@ -57,6 +57,11 @@ def compare(got, want, suffixes, rtol=1e-5, atol=0.0):
         else:
             with np.errstate(all="ignore"):
                 ok = np.isclose(g, w, rtol=rtol, atol=atol) | both_nan | ((g == w))
+        if 'attr_"stderr"' in suf:
+            # scipy.stats.linregress on exactly two points: stderr = sqrt((1-r^2)*ssym/ssxm/0) is NaN when
+            # r rounds to +-1 and inf when it rounds to 0.999..; the reference itself is rounding-chaotic
+            # here (DESIGN.md "known reference instabilities"), so NaN and inf are treated as the same answer.
+            ok = ok | ((np.isnan(g) | np.isinf(g)) & (np.isnan(w) | np.isinf(w)))
         for r in np.nonzero(~ok)[0]:
             bad.append((int(r), suf, float(g[r]), float(w[r])))
     return bad

@@ -1,0 +1,90 @@
+"""GPU parity per kernel group (SORTED, SPECTRAL, LA, ENTROPY, SEQ) and for the full settings objects,
+through the C ABI (CSR entry point), against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from tests.helpers import gpu_vs_oracle, synthetic_series
+from tsfresh_b200.settings import ComprehensiveFCParameters, EfficientFCParameters
+
+pytestmark = pytest.mark.gpu
+
+GROUPS = {
+    "sorted": ["symmetry_looking", "has_duplicate", "median", "percentage_of_reoccurring_values_to_all_values",
+               "percentage_of_reoccurring_datapoints_to_all_datapoints", "sum_of_reoccurring_values",
+               "sum_of_reoccurring_data_points", "ratio_value_number_to_time_series_length", "quantile",
+               "mean_n_absolute_max", "change_quantiles", "friedrich_coefficients", "max_langevin_fixed_point"],
+    "spectral": ["fft_coefficient", "fft_aggregated", "spkt_welch_density", "fourier_entropy", "cwt_coefficients"],
+    "la": ["ar_coefficient", "augmented_dickey_fuller"],
+    "entropy": ["sample_entropy", "approximate_entropy"],
+    "seq": ["lempel_ziv_complexity", "permutation_entropy", "number_cwt_peaks"],
+}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from tsfresh_b200._lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def settings_of(names):
+    full = ComprehensiveFCParameters()
+    return {k: full[k] for k in full if k in names}
+
+
+def _report(bad):
+    return "\n".join("row %d %s: gpu=%r oracle=%r" % b for b in bad[:40]) + "\n(%d mismatches)" % len(bad)
+
+
+def short_and_ragged():
+    rng = np.random.default_rng(5)
+    series = [rng.standard_normal(n).astype(np.float32) for n in (1, 2, 3, 4, 5, 8, 12, 20, 31, 32, 33, 63, 64, 65, 200, 600)]
+    series += [np.zeros(10, np.float32), np.ones(7, np.float32), np.array([1, 1, 2, 2, 3, 3, 3], np.float32),
+               np.array([5.0], np.float32), np.array([-1, 1] * 20, np.float32), np.arange(50, dtype=np.float32)]
+    return series
+
+
+@pytest.mark.parametrize("group", list(GROUPS))
+@pytest.mark.parametrize("kind,length", [("normal", 256), ("walk", 256), ("normal", 100), ("walk", 1024), ("normal", 37)])
+def test_group(ctx, group, kind, length):
+    count = 12 if length >= 1024 else 40
+    series = list(synthetic_series(100 + length, count, length, kind))
+    bad, *_ = gpu_vs_oracle(ctx, settings_of(GROUPS[group]), series)
+    assert not bad, _report(bad)
+
+
+@pytest.mark.parametrize("group", ["sorted", "spectral", "la", "entropy"])
+def test_group_short_and_ragged(ctx, group):
+    bad, *_ = gpu_vs_oracle(ctx, settings_of(GROUPS[group]), short_and_ragged())
+    assert not bad, _report(bad)
+
+
+def test_seq_short_and_ragged(ctx):
+    # permutation_entropy on tied windows is implementation-defined in the reference (numpy's default
+    # argsort is not stable: SURVEY.md section 8a row 58); tie-free inputs only.
+    rng = np.random.default_rng(9)
+    series = [rng.standard_normal(n).astype(np.float32) for n in (1, 2, 3, 4, 5, 8, 12, 20, 31, 32, 33, 63, 64, 65, 200, 600)]
+    bad, *_ = gpu_vs_oracle(ctx, settings_of(GROUPS["seq"]), series)
+    assert not bad, _report(bad)
+
+
+def test_sorted_with_ties(ctx):
+    series = list(synthetic_series(3, 40, 200, "rounded"))
+    bad, *_ = gpu_vs_oracle(ctx, settings_of(GROUPS["sorted"]), series)
+    assert not bad, _report(bad)
+
+
+@pytest.mark.parametrize("kind,length,count", [("normal", 256, 64), ("walk", 128, 32), ("normal", 1024, 8)])
+def test_comprehensive(ctx, kind, length, count):
+    series = list(synthetic_series(42, count, length, kind))
+    bad, plan, got, want = gpu_vs_oracle(ctx, ComprehensiveFCParameters(), series)
+    assert plan.n_cols == 783
+    assert not bad, _report(bad)
+
+
+def test_efficient(ctx):
+    series = list(synthetic_series(43, 64, 256))
+    bad, plan, got, want = gpu_vs_oracle(ctx, EfficientFCParameters(), series)
+    assert plan.n_cols == 777
+    assert not bad, _report(bad)

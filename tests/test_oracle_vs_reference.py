@@ -1,0 +1,63 @@
+"""Pins the oracle (oracle/calculators.py) and the plan compiler's column names against the UNMODIFIED
+reference imported from /root/reference (build container only; skipped on the GPU box)."""
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import ref_shim
+from oracle.extract import compare, oracle_rows
+from tests.helpers import synthetic_series
+from tsfresh_b200.plan import Plan
+from tsfresh_b200.settings import ComprehensiveFCParameters, EfficientFCParameters, MinimalFCParameters
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+
+
+def reference_frame(series, settings):
+    ref_shim.load()
+    from tsfresh.feature_extraction import extract_features
+    ids = np.concatenate([np.full(len(s), i) for i, s in enumerate(series)])
+    t = np.concatenate([np.arange(len(s)) for s in series])
+    v = np.concatenate([np.asarray(s, np.float32).astype(np.float64) for s in series])
+    df = pd.DataFrame({"id": ids, "time": t, "value": v})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return extract_features(df, column_id="id", column_sort="time", default_fc_parameters=settings, n_jobs=0,
+                                disable_progressbar=True)
+
+
+def test_settings_match_reference():
+    ref_shim.load()
+    from tsfresh.feature_extraction import settings as rs
+    for mine, theirs in ((ComprehensiveFCParameters(), rs.ComprehensiveFCParameters()),
+                         (EfficientFCParameters(), rs.EfficientFCParameters()),
+                         (MinimalFCParameters(), rs.MinimalFCParameters())):
+        assert list(mine.keys()) == list(theirs.keys())
+        for k in mine:
+            assert mine[k] == theirs[k], k
+
+
+@pytest.mark.parametrize("kind,length,count", [("normal", 256, 6), ("walk", 100, 4), ("rounded", 64, 4), ("normal", 1300, 2)])
+def test_oracle_matches_reference(kind, length, count):
+    series = list(synthetic_series(11, count, length, kind))
+    settings = ComprehensiveFCParameters()
+    X = reference_frame(series, settings)
+    plan = Plan(settings)
+    assert ["value__" + s for s in plan.suffixes] == list(X.columns)
+    mine = oracle_rows([s.astype(np.float64) for s in series], settings)
+    bad = compare(mine, X.to_numpy(dtype=np.float64), plan.suffixes, rtol=1e-12)
+    assert not bad, bad[:20]
+
+
+def test_oracle_matches_reference_short_series():
+    rng = np.random.default_rng(3)
+    series = [rng.standard_normal(n).astype(np.float32) for n in (1, 2, 3, 4, 5, 8, 12, 20, 23, 31, 40)]
+    series += [np.zeros(9, np.float32), np.ones(5, np.float32), np.array([1, 1, 2, 2, 3, 3, 3], np.float32)]
+    settings = ComprehensiveFCParameters()
+    X = reference_frame(series, settings)
+    plan = Plan(settings)
+    mine = oracle_rows([s.astype(np.float64) for s in series], settings)
+    bad = compare(mine, X.to_numpy(dtype=np.float64), plan.suffixes, rtol=1e-12)
+    assert not bad, bad[:20]

@@ -1,0 +1,142 @@
+// k_entropy.cu -- kernel group ENTROPY: sample_entropy (feature_calculators.py:1701-1754) and
+// approximate_entropy with m = 2 (feature_calculators.py:1759-1805) -- the O(n^2) "class Q" rows.
+//
+// Both need, for a tolerance tau and every template start i, the number of template starts j whose
+// Chebyshev distance is <= tau, for templates of length 2 (i, j in [0, n-2]) and of length 3
+// (i, j in [0, n-3]).  One warp per series; lane = row i, sequential sweep over j with the three
+// neighbouring samples in registers; up to NT tolerances are evaluated in the same sweep so the
+// distances are formed once.  Differences are float64 of float32-origin values, i.e. the very same
+// IEEE operations numpy performs, so the counts are bit-identical to the reference's.
+#include <algorithm>
+
+#include "tsfx_common.cuh"
+#include "tsfx_kernels.h"
+
+namespace tsfx {
+
+template <int NT>
+__device__ __forceinline__ void entropy_sweep(const double* xd, int n, const double (&tau)[NT], double (&sum_ln2)[NT],
+                                              double (&sum_ln3)[NT], double (&sumB)[NT], double (&sumA)[NT], int lane) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { sum_ln2[t] = 0.0; sum_ln3[t] = 0.0; sumB[t] = 0.0; sumA[t] = 0.0; }
+    const int n2 = n - 1, n3 = n - 2;          // number of length-2 / length-3 templates
+    if (n2 <= 0) return;
+    const double inv2 = 1.0 / (double)n2, inv3 = n3 > 0 ? 1.0 / (double)n3 : 0.0;
+    for (int r0 = 0; r0 < n2; r0 += 32) {
+        const int i = r0 + lane;
+        const bool v2 = i < n2, v3 = i < n3;
+        const double a0 = v2 ? xd[i] : 0.0, a1 = v2 ? xd[i + 1] : 0.0, a2 = v3 ? xd[i + 2] : 0.0;
+        int c2[NT], c3[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { c2[t] = 0; c3[t] = 0; }
+        double b0 = xd[0], b1 = xd[1];
+        for (int j = 0; j < n3; ++j) {
+            const double b2 = xd[j + 2];
+            const double m2 = fmax(fabs(a0 - b0), fabs(a1 - b1));
+            const double m3 = fmax(m2, fabs(a2 - b2));
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { c2[t] += (m2 <= tau[t]); c3[t] += (m3 <= tau[t]); }
+            b0 = b1; b1 = b2;
+        }
+        {   // last length-2 template j = n2 - 1
+            const double m2 = fmax(fabs(a0 - b0), fabs(a1 - b1));
+#pragma unroll
+            for (int t = 0; t < NT; ++t) c2[t] += (m2 <= tau[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (v2) { sum_ln2[t] += log((double)c2[t] * inv2); sumB[t] += (double)(c2[t] - 1); }
+            if (v3) { sum_ln3[t] += log((double)c3[t] * inv3); sumA[t] += (double)(c3[t] - 1); }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        sum_ln2[t] = wsum(sum_ln2[t]);
+        sum_ln3[t] = wsum(sum_ln3[t]);
+        sumB[t] = wsum(sumB[t]);
+        sumA[t] = wsum(sumA[t]);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void entropy_batch(const Desc* descs, int j0, int cnt, const double* xd, int n, double sd,
+                                              double* orow, int lane) {
+    double tau[NT], l2[NT], l3[NT], sB[NT], sA[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        if (t < cnt) {
+            const Desc d = descs[j0 + t];
+            tau[t] = (d.calc == TSFX_SAMPLE_ENTROPY) ? 0.2 * sd : d.p0 * sd;
+        } else tau[t] = -1.0;
+    }
+    entropy_sweep<NT>(xd, n, tau, l2, l3, sB, sA, lane);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        if (t < cnt) {
+            const Desc d = descs[j0 + t];
+            double r;
+            if (d.calc == TSFX_SAMPLE_ENTROPY) r = -log(sA[t] / sB[t]);
+            else if (n <= 3) r = 0.0;                                  // N <= m + 1
+            else r = fabs(l2[t] / (double)(n - 1) - l3[t] / (double)(n - 2));
+            if (lane == 0) orow[d.col] = r;
+        }
+    }
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_entropy(EntropyArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    double* xd = reinterpret_cast<double*>(base);
+    float* xs = reinterpret_cast<float*>(xd + A.npad + 2);
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+        const int n = load_series(A.R, s, xs, lane);
+        const Moments M = moments(xs, n, nullptr, lane);
+        for (int i = lane; i < n + 2; i += 32) xd[i] = i < n ? (double)xs[i] : 0.0;
+        __syncwarp();
+        double* orow = A.out + (size_t)s * A.ncols;
+        int j = 0;
+        while (j < A.nd) {
+            int left = A.nd - j;
+            if (left >= 6) { entropy_batch<6>(A.descs, j, 6, xd, n, M.sd, orow, lane); j += 6; }
+            else if (left > 3) { entropy_batch<6>(A.descs, j, left, xd, n, M.sd, orow, lane); j += left; }
+            else if (left == 3) { entropy_batch<3>(A.descs, j, 3, xd, n, M.sd, orow, lane); j += 3; }
+            else if (left == 2) { entropy_batch<2>(A.descs, j, 2, xd, n, M.sd, orow, lane); j += 2; }
+            else { entropy_batch<1>(A.descs, j, 1, xd, n, M.sd, orow, lane); j += 1; }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, int sm_count) {
+    EntropyArgs A = A0;
+    A.npad = (max_len + 3) & ~3;
+    size_t per = (size_t)(A.npad + 2) * 8 + (size_t)A.npad * 4;
+    per = (per + 15) & ~(size_t)15;
+    A.bytes_per_warp = (int)per;
+    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
+    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 64 * 1024 / per));
+    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
+    size_t smem = per * wpc;
+    int64_t cap = (int64_t)sm_count * 32;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
+#define TSFX_LAUNCH(W)                                                                                      \
+    {                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(k_entropy<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                     \
+        k_entropy<W><<<grid, W * 32, smem, st>>>(A);                                                        \
+    }
+    switch (wpc) {
+        case 8: TSFX_LAUNCH(8) break;
+        case 4: TSFX_LAUNCH(4) break;
+        case 2: TSFX_LAUNCH(2) break;
+        default: TSFX_LAUNCH(1) break;
+    }
+#undef TSFX_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace tsfx

@@ -1,0 +1,387 @@
+// k_seq.cu -- kernel group SEQ: the inherently sequential / dictionary calculators
+//   lempel_ziv_complexity (feature_calculators.py:1825-1862)   lane-per-parameter trie parse
+//   permutation_entropy   (feature_calculators.py:1866-1915)   rank codes -> bitonic sort -> run lengths
+//   number_cwt_peaks      (feature_calculators.py:1320-1339; scipy.signal.find_peaks_cwt with _ricker :1307)
+//
+// One warp per series.  Shared memory per warp (doubles first): row0[npad], tmp[npad] (cwt rows),
+// hw[TSFX_MAXW_PTS] (wavelet taps), then uint32 codes[npow2], uint16 trie[LZ_LANES][3][npad+1],
+// uint32 maxbits[TSFX_CWT_MAXN][npad/32+1], int16 line tables [5][2*npad], float xs[npad].
+#include <algorithm>
+
+#include "tsfx_common.cuh"
+#include "tsfx_kernels.h"
+
+namespace tsfx {
+
+#define TSFX_CWT_MAXN 16
+#define TSFX_MAXW_PTS 160
+#define LZ_LANES 8
+
+struct SeqLayout {
+    int npad, npow2, nwords, lz_lanes, cwt_n;
+    int off_tmp, off_hw, off_codes, off_trie, off_bits, off_lines, off_map, off_xs;   // byte offsets
+};
+
+// ---------------------------------------------------------------------------- Lempel-Ziv
+// symbol = np.searchsorted(np.linspace(min, max, bins+1)[1:], x, side="left")
+__device__ __forceinline__ int lz_symbol(double v, double vmin, double vmax, double step, int bins) {
+    int c = (int)__ddiv_rn(__dsub_rn(v, vmin), step);      // NaN (step == 0) converts to 0
+    if (c < 0) c = 0;
+    if (c > bins) c = bins;
+    // edge(i) = i*step + vmin for i < bins, edge(bins) = vmax ; count edges i in 1..bins with edge(i) < v
+    while (c < bins) {
+        double e = (c + 1 == bins) ? vmax : __dadd_rn(__dmul_rn((double)(c + 1), step), vmin);
+        if (e < v) ++c; else break;
+    }
+    while (c > 0) {
+        double e = (c == bins) ? vmax : __dadd_rn(__dmul_rn((double)c, step), vmin);
+        if (!(e < v)) --c; else break;
+    }
+    return c;
+}
+
+// ---------------------------------------------------------------------------- bitonic sort on uint32
+__device__ __forceinline__ void warp_bitonic_sort_u32(unsigned* s, int m, int lane) {
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (m >> 1); t += 32) {
+                int i = 2 * t - (t & (j - 1));
+                int l = i + j;
+                unsigned a = s[i], b = s[l];
+                bool up = (i & k) == 0;
+                if ((a > b) == up) { s[i] = b; s[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- find_peaks_cwt pieces
+// value of cwt row (width w) at column i: convolve(x, ricker(min(10w, n), w), mode="same")[i]
+__device__ __forceinline__ double cwt_value(const float* xs, int n, const double* hw, int npts, int i) {
+    const int c0 = (npts - 1) / 2;
+    // same[i] = sum_t x[t] h[i + c0 - t], 0 <= i + c0 - t < npts
+    int t_lo = i + c0 - (npts - 1);
+    if (t_lo < 0) t_lo = 0;
+    int t_hi = i + c0;
+    if (t_hi > n - 1) t_hi = n - 1;
+    double a = 0.0;
+    for (int t = t_lo; t <= t_hi; ++t) a = fma((double)xs[t], hw[i + c0 - t], a);
+    return a;
+}
+
+__device__ __forceinline__ void ricker_fill(double* hw, int npts, int w, int lane) {
+    // _ricker(points, a) (:1307-1316)
+    const double a = (double)w;
+    const double A = 2.0 / (sqrt(3.0 * a) * pow(3.14159265358979323846, 0.25));
+    const double wsq = a * a;
+    for (int v = lane; v < npts; v += 32) {
+        double vec = (double)v - ((double)npts - 1.0) / 2.0;
+        double xsq = vec * vec;
+        double mod = 1.0 - xsq / wsq;
+        double gauss = exp(-xsq / (2.0 * wsq));
+        hw[v] = A * mod * gauss;
+    }
+    __syncwarp();
+}
+
+// scipy.stats.scoreatpercentile(window, 10) with the window copied into `buf` (<= wlen values), one lane
+__device__ __forceinline__ double percentile10(double* buf, int wlen) {
+    for (int a = 1; a < wlen; ++a) {           // insertion sort
+        double v = buf[a];
+        int b = a - 1;
+        while (b >= 0 && buf[b] > v) { buf[b + 1] = buf[b]; --b; }
+        buf[b + 1] = v;
+    }
+    double idx = 10.0 / 100.0 * (double)(wlen - 1);
+    int i = (int)idx;
+    if ((double)i == idx) return buf[i];
+    double w0 = (double)(i + 1) - idx, w1 = idx - (double)i;
+    return (buf[i] * w0 + buf[i + 1] * w1) / (w0 + w1);
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    double* row0 = reinterpret_cast<double*>(base);
+    double* tmp = reinterpret_cast<double*>(base + Y.off_tmp);
+    double* hw = reinterpret_cast<double*>(base + Y.off_hw);
+    unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
+    unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
+    unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
+    short* lines = reinterpret_cast<short*>(base + Y.off_lines);
+    short* colmap = reinterpret_cast<short*>(base + Y.off_map);
+    float* xs = reinterpret_cast<float*>(base + Y.off_xs);
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+    const int LCAP = 2 * Y.npad;
+
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+        const int n = load_series(A.R, s, xs, lane);
+        double* orow = A.out + (size_t)s * A.ncols;
+        float lo = INFINITY, hi = -INFINITY;
+        for (int i = lane; i < n; i += 32) { lo = fminf(lo, xs[i]); hi = fmaxf(hi, xs[i]); }
+        const double vmin = (double)wminf(lo), vmax = (double)wmaxf(hi);
+        bool cwt_ready = false;
+
+        int j = 0;
+        while (j < A.nd) {
+            const Desc d0 = A.descs[j];
+            if (d0.calc == TSFX_LEMPEL_ZIV_COMPLEXITY) {
+                // up to lz_lanes consecutive LZ descriptors, one per lane
+                int cnt = 0;
+                while (j + cnt < A.nd && cnt < Y.lz_lanes && A.descs[j + cnt].calc == TSFX_LEMPEL_ZIV_COMPLEXITY) ++cnt;
+                if (lane < cnt) {
+                    const Desc d = A.descs[j + lane];
+                    const int bins = d.i0;
+                    const double step = __ddiv_rn(__dsub_rn(vmax, vmin), (double)bins);
+                    unsigned short* first = trie + (size_t)lane * 3 * (Y.npad + 1);
+                    unsigned short* next = first + (Y.npad + 1);
+                    unsigned short* sym = next + (Y.npad + 1);
+                    int nodes = 1, node = 0, phrases = 0;
+                    first[0] = 0;                                   // 0 = no child (root is node 0)
+                    for (int pos = 0; pos < n; ++pos) {
+                        int sy = lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                        int ch = first[node];
+                        while (ch != 0 && sym[ch] != sy) ch = next[ch];
+                        if (ch != 0) node = ch;
+                        else {
+                            int nn = nodes++;
+                            sym[nn] = (unsigned short)sy;
+                            first[nn] = 0;
+                            next[nn] = first[node];
+                            first[node] = (unsigned short)nn;
+                            ++phrases;
+                            node = 0;
+                        }
+                    }
+                    orow[d.col] = (double)phrases / (double)n;
+                }
+                __syncwarp();
+                j += cnt;
+            } else if (d0.calc == TSFX_PERMUTATION_ENTROPY) {
+                const int tau = d0.i0, D = d0.i1;
+                double r = dnan();
+                if (n >= D) {
+                    const int W = (n - D) / tau + 1;
+                    int m = 2;
+                    while (m < W) m <<= 1;
+                    for (int k = lane; k < m; k += 32) {
+                        unsigned code = 0xffffffffu;
+                        if (k < W) {
+                            const float* w = xs + (size_t)k * tau;
+                            code = 0;
+                            unsigned mul = 1;
+                            for (int p = 0; p < D; ++p) {
+                                float wp = w[p];
+                                unsigned rk = 0;
+                                for (int q = 0; q < D; ++q) { float wq = w[q]; rk += (wq < wp) || (wq == wp && q < p); }
+                                code += rk * mul;
+                                mul *= (unsigned)D;
+                            }
+                        }
+                        codes[k] = code;
+                    }
+                    __syncwarp();
+                    warp_bitonic_sort_u32(codes, m, lane);
+                    double acc = 0.0;
+                    for (int k = lane; k < W; k += 32) {
+                        unsigned c = codes[k];
+                        if (k == 0 || codes[k - 1] != c) {
+                            int len = 1;
+                            while (k + len < W && codes[k + len] == c) ++len;
+                            double p = (double)len / (double)W;
+                            acc += p * log(p);
+                        }
+                    }
+                    r = -wsum(acc);
+                    __syncwarp();
+                }
+                if (lane == 0) orow[d0.col] = r;
+                ++j;
+            } else if (d0.calc == TSFX_NUMBER_CWT_PEAKS) {
+                if (!cwt_ready) {
+                    // all rows 1..cwt_n once: local-maximum bit masks per row, row of width 1 kept in row0
+                    for (int w = 1; w <= Y.cwt_n; ++w) {
+                        const int npts = min(10 * w, n);
+                        ricker_fill(hw, npts, w, lane);
+                        double* dst = (w == 1) ? row0 : tmp;
+                        for (int i = lane; i < n; i += 32) dst[i] = cwt_value(xs, n, hw, npts, i);
+                        __syncwarp();
+                        unsigned* bits = maxbits + (size_t)(w - 1) * Y.nwords;
+                        for (int b0 = 0; b0 < n; b0 += 32) {
+                            int i = b0 + lane;
+                            bool mx = false;
+                            if (i < n) {
+                                double v = dst[i];
+                                double pl = dst[min(i + 1, n - 1)], mi = dst[max(i - 1, 0)];
+                                mx = (v > pl) && (v > mi);
+                            }
+                            unsigned word = __ballot_sync(FULL, mx);
+                            if (lane == 0) bits[b0 >> 5] = word;
+                        }
+                        __syncwarp();
+                    }
+                    cwt_ready = true;
+                }
+                const int nrows = d0.i0;
+                int result = 0;
+                if (lane == 0) {
+                    short* l_last = lines;                 // last attached column
+                    short* l_gap = lines + LCAP;
+                    short* l_len = lines + 2 * LCAP;
+                    short* l_minrow = lines + 3 * LCAP;    // smallest row so far
+                    short* l_mincol = lines + 4 * LCAP;    // first column attached at that row
+                    const int min_length = (nrows + 3) / 4;                       // ceil(nrows / 4)
+                    const int window = (n + 19) / 20;                             // ceil(n / 20)
+                    const int hf = window / 2, odd = window & 1;
+                    int nl = 0;
+                    // evaluates the filter of _filter_ridge_lines for one finished line
+                    auto accept = [&](int li) -> bool {
+                        if (l_len[li] < min_length) return false;
+                        const int rr = l_minrow[li], cc = l_mincol[li];
+                        double val;
+                        if (rr == 0) val = row0[cc];
+                        else {
+                            const int w = rr + 1, npts = min(10 * w, n);
+                            // recompute the ricker taps of that width on the fly (one lane)
+                            const double a = (double)w, Aa = 2.0 / (sqrt(3.0 * a) * pow(3.14159265358979323846, 0.25));
+                            const int c0 = (npts - 1) / 2;
+                            int t_lo = max(cc + c0 - (npts - 1), 0), t_hi = min(cc + c0, n - 1);
+                            double acc = 0.0;
+                            for (int t = t_lo; t <= t_hi; ++t) {
+                                double vec = (double)(cc + c0 - t) - ((double)npts - 1.0) / 2.0;
+                                double xsq = vec * vec;
+                                double h = Aa * (1.0 - xsq / (a * a)) * exp(-xsq / (2.0 * a * a));
+                                acc = fma((double)xs[t], h, acc);
+                            }
+                            val = acc;
+                        }
+                        const int ws = max(cc - hf, 0), we = min(cc + hf + odd, n);
+                        for (int q = ws; q < we; ++q) tmp[q - ws] = row0[q];
+                        const double noise = percentile10(tmp, we - ws);
+                        const double snr = fabs(val / noise);
+                        return !(snr < 1.0);
+                    };
+                    // start row: the largest row that has any local maximum
+                    int start = -1;
+                    for (int r = nrows - 1; r >= 0 && start < 0; --r) {
+                        const unsigned* bits = maxbits + (size_t)r * Y.nwords;
+                        for (int wd = 0; wd < Y.nwords; ++wd) if (bits[wd]) { start = r; break; }
+                    }
+                    if (start >= 0) {
+                        {
+                            const unsigned* bits = maxbits + (size_t)start * Y.nwords;
+                            for (int c = 0; c < n; ++c)
+                                if ((bits[c >> 5] >> (c & 31)) & 1u) {
+                                    if (nl < LCAP) { l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)start; l_mincol[nl] = (short)c; ++nl; }
+                                }
+                        }
+                        for (int r = start - 1; r >= 0; --r) {
+                            const unsigned* bits = maxbits + (size_t)r * Y.nwords;
+                            const int maxd = (r + 1) / 4;                  // floor(widths[r] / 4), diffs are integers
+                            // snapshot: column -> first line (list order) whose last column is that column
+                            for (int c = 0; c < n; ++c) colmap[c] = -1;
+                            for (int li = nl - 1; li >= 0; --li) { l_gap[li] += 1; colmap[l_last[li]] = (short)li; }
+                            const int nl_snapshot = nl;
+                            for (int c = 0; c < n; ++c) {
+                                if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
+                                int best = -1;
+                                if (nl_snapshot > 0) {
+                                    // np.argmin(|c - prev|): the smallest distance wins, first in list order on
+                                    // ties; the point attaches only when that distance is <= max_distances[row]
+                                    for (int dd = 0; dd <= maxd && best < 0; ++dd) {
+                                        int a = (c - dd >= 0) ? colmap[c - dd] : -1;
+                                        int b = (dd > 0 && c + dd < n) ? colmap[c + dd] : -1;
+                                        if (a >= 0 && b >= 0) best = a < b ? a : b;
+                                        else if (a >= 0) best = a;
+                                        else if (b >= 0) best = b;
+                                    }
+                                }
+                                if (best >= 0) {
+                                    l_last[best] = (short)c;
+                                    l_gap[best] = 0;
+                                    l_len[best] += 1;
+                                    if (r < l_minrow[best]) { l_minrow[best] = (short)r; l_mincol[best] = (short)c; }
+                                } else if (nl < LCAP) {
+                                    l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)r; l_mincol[nl] = (short)c; ++nl;
+                                }
+                            }
+                            // retire lines whose gap exceeds gap_thresh = ceil(widths[0]) = 1 (order preserved)
+                            int keep = 0;
+                            for (int li = 0; li < nl; ++li) {
+                                if (l_gap[li] > 1) { if (accept(li)) ++result; }
+                                else {
+                                    if (keep != li) { l_last[keep] = l_last[li]; l_gap[keep] = l_gap[li]; l_len[keep] = l_len[li]; l_minrow[keep] = l_minrow[li]; l_mincol[keep] = l_mincol[li]; }
+                                    ++keep;
+                                }
+                            }
+                            nl = keep;
+                        }
+                        for (int li = 0; li < nl; ++li) if (accept(li)) ++result;
+                    }
+                    orow[d0.col] = (double)result;
+                }
+                __syncwarp();
+                ++j;
+            } else {
+                if (lane == 0) orow[d0.col] = dnan();
+                ++j;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
+    SeqArgs A = A0;
+    A.npad = (max_len + 3) & ~3;
+    SeqLayout Y;
+    Y.npad = A.npad;
+    int p2 = 2;
+    while (p2 < max_len) p2 <<= 1;
+    Y.npow2 = p2;
+    Y.nwords = (A.npad + 31) / 32 + 1;
+    // which pieces does this plan need?  (nscr carries flags from the API: bit0 lz, bit1 perm, bits 8.. cwt_n)
+    const bool need_lz = (A.nscr & 1) != 0, need_perm = (A.nscr & 2) != 0;
+    Y.cwt_n = (A.nscr >> 8) & 0xff;
+    Y.lz_lanes = need_lz ? LZ_LANES : 0;
+    size_t off = 0;
+    const bool need_cwt = Y.cwt_n > 0;
+    off += need_cwt ? (size_t)A.npad * 8 : 0;              // row0
+    Y.off_tmp = (int)off;   off += need_cwt ? (size_t)A.npad * 8 : 0;
+    Y.off_hw = (int)off;    off += need_cwt ? (size_t)TSFX_MAXW_PTS * 8 : 0;
+    Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
+    Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * 3 * (A.npad + 1) * 2;
+    off = (off + 3) & ~(size_t)3;
+    Y.off_bits = (int)off;  off += need_cwt ? (size_t)Y.cwt_n * Y.nwords * 4 : 0;
+    Y.off_lines = (int)off; off += need_cwt ? (size_t)5 * 2 * A.npad * 2 : 0;
+    Y.off_map = (int)off;   off += need_cwt ? (size_t)A.npad * 2 : 0;
+    off = (off + 15) & ~(size_t)15;
+    Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
+    size_t per = (off + 15) & ~(size_t)15;
+    A.bytes_per_warp = (int)per;
+    if (per > 227 * 1024 || max_len > 32000) return cudaErrorInvalidConfiguration;
+    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 100 * 1024 / per));
+    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
+    size_t smem = per * wpc;
+    int64_t cap = (int64_t)sm_count * 16;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
+#define TSFX_LAUNCH(W)                                                                                  \
+    {                                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(k_seq<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                 \
+        k_seq<W><<<grid, W * 32, smem, st>>>(A, Y);                                                     \
+    }
+    switch (wpc) {
+        case 8: TSFX_LAUNCH(8) break;
+        case 4: TSFX_LAUNCH(4) break;
+        case 2: TSFX_LAUNCH(2) break;
+        default: TSFX_LAUNCH(1) break;
+    }
+#undef TSFX_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace tsfx

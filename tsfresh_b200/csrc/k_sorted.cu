@@ -1,0 +1,306 @@
+// k_sorted.cu -- kernel group SORTED: every calculator that needs an ordered copy of the series
+// ("class S" rows of SURVEY.md section 8a): median, quantile, symmetry_looking, has_duplicate, the
+// re-occurring-value family, mean_n_absolute_max, change_quantiles, friedrich_coefficients,
+// max_langevin_fixed_point.
+//
+// One warp per series; one in-shared-memory bitonic sort (float32 keys, +inf padding) shared by all of
+// them.  Shared memory per warp: xs[npad] (time order), srt[npow2] (ascending), scr[nscr] float64.
+#include <algorithm>
+
+#include "tsfx_common.cuh"
+#include "tsfx_kernels.h"
+#include "tsfx_math.cuh"
+
+namespace tsfx {
+
+__device__ __forceinline__ void warp_bitonic_sort(float* s, int m, int lane) {
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (m >> 1); t += 32) {
+                int i = 2 * t - (t & (j - 1));
+                int l = i + j;
+                float a = s[i], b = s[l];
+                bool up = (i & k) == 0;
+                if ((a > b) == up) { s[i] = b; s[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct Uniq { int n_unique, n_reocc_values, n_reocc_points; double sum_reocc_values, sum_reocc_points; bool any_dup; };
+
+__device__ __forceinline__ Uniq unique_pass(const float* s, int n, int lane) {
+    int nu = 0, nrv = 0, nrp = 0;
+    double srv = 0.0, srp = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        float v = s[i];
+        bool eq_prev = i > 0 && s[i - 1] == v;
+        bool eq_next = i + 1 < n && s[i + 1] == v;
+        bool second = eq_prev && !(i > 1 && s[i - 2] == v);
+        nu += !eq_prev;
+        if (second) { ++nrv; srv += (double)v; }
+        if (eq_prev || eq_next) { ++nrp; srp += (double)v; }
+    }
+    Uniq U;
+    U.n_unique = wsumi(nu);
+    U.n_reocc_values = wsumi(nrv);
+    U.n_reocc_points = wsumi(nrp);
+    U.sum_reocc_values = wsum(srv);
+    U.sum_reocc_points = wsum(srp);
+    U.any_dup = U.n_unique != n;
+    return U;
+}
+
+// sorted copy of x[:-1] expressed as a view on the full sorted array with one instance of x[n-1] removed
+struct DropLast {
+    const float* s;
+    int pos;
+    __device__ __forceinline__ float operator[](int j) const { return s[j + (j >= pos ? 1 : 0)]; }
+};
+
+__device__ __forceinline__ double quantile_view(const DropLast& v, int n, double q) {
+    double posf = q * (double)(n - 1);
+    double fl = floor(posf);
+    int lo = (int)fl;
+    if (lo < 0) lo = 0;
+    if (lo > n - 1) lo = n - 1;
+    int hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
+    double t = posf - fl;
+    double a = (double)v[lo], b = (double)v[hi];
+    double d = b - a;
+    if (t >= 0.5) return b - d * (1.0 - t);
+    return a + d * t;
+}
+
+// Estimates the Friedrich cubic (feature_calculators.py:131-173 with m = 3): returns in all lanes
+// whether a coefficient vector exists; coefficients land in coef[0..3] (shared memory).
+__device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt, int n, int r, double* scr, double* coef,
+                                              int lane) {
+    const int n1 = n - 1;                        // length of signal = x[:-1]
+    if (n1 < 1) return false;
+    double* edges = scr;                         // r + 1
+    double* cnt = edges + (r + 1);               // r
+    double* sx = cnt + r;                        // r
+    double* sy = sx + r;                         // r
+    // position of one instance of x[n-1] inside the sorted array
+    const float last = xs[n - 1];
+    int pos = 0x7fffffff;
+    for (int b0 = 0; b0 < n && pos == 0x7fffffff; b0 += 32) {
+        int i = b0 + lane;
+        unsigned hit = __ballot_sync(FULL, i < n && srt[i] == last);
+        if (hit) pos = b0 + __ffs(hit) - 1;
+    }
+    DropLast view{srt, pos};
+    // quantile levels of pd.qcut(x, r): linspace(0, 1, r+1), bumped to the next double where r*q != i
+    const double step = __ddiv_rn(1.0, (double)r);
+    for (int i = lane; i <= r; i += 32) {
+        double q = (i == r) ? 1.0 : __dmul_rn((double)i, step);
+        if (__dmul_rn((double)r, q) != (double)i) q = nextafter(q, 1.0);
+        edges[i] = quantile_view(view, n1, q);
+    }
+    for (int i = lane; i < r; i += 32) { cnt[i] = 0.0; sx[i] = 0.0; sy[i] = 0.0; }
+    __syncwarp();
+    bool dup = false;
+    for (int i = lane; i < r; i += 32) dup |= (edges[i] == edges[i + 1]);
+    if (__any_sync(FULL, dup) && r + 1 != 2) return false;      // "Bin edges must be unique" -> NaN
+    for (int j = lane; j < n1; j += 32) {
+        double v = (double)xs[j];
+        double dl = (double)xs[j + 1] - v;
+        // ids = searchsorted(edges, v, side="left") ; include_lowest: v == edges[0] -> 1
+        int lo = 0, hi = r + 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (edges[mid] < v) lo = mid + 1; else hi = mid; }
+        int id = lo;
+        if (v == edges[0]) id = 1;
+        if (id >= 1 && id <= r) {
+            atomicAdd(&cnt[id - 1], 1.0);
+            atomicAdd(&sx[id - 1], v);
+            atomicAdd(&sy[id - 1], dl);
+        }
+    }
+    __syncwarp();
+    int ok = 0;
+    if (lane == 0) {
+        int k = 0;
+        for (int b = 0; b < r; ++b) {
+            double c = cnt[b];
+            if (c > 0.0) { double mx = sx[b] / c, my = sy[b] / c; sx[k] = mx; sy[k] = my; ++k; }
+        }
+        double c4[4];
+        ok = (k > 0 && m_polyfit3(sx, sy, k, c4)) ? 1 : 0;
+        if (ok) { coef[0] = c4[0]; coef[1] = c4[1]; coef[2] = c4[2]; coef[3] = c4[3]; }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    __syncwarp();
+    return ok != 0;
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    double* scr = reinterpret_cast<double*>(base);
+    float* xs = reinterpret_cast<float*>(scr + A.nscr);
+    float* srt = xs + A.npad;
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+        const int n = load_series(A.R, s, xs, lane);
+        int m = 1;
+        while (m < n) m <<= 1;
+        double sum = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            float v = i < n ? xs[i] : INFINITY;
+            srt[i] = v;
+            if (i < n) sum += (double)v;
+        }
+        sum = wsum(sum);
+        __syncwarp();
+        warp_bitonic_sort(srt, m, lane);
+        const double dn = (double)n;
+        const double mean = sum / dn;
+        const double vmin = (double)srt[0], vmax = (double)srt[n - 1];
+        const double med = (n & 1) ? (double)srt[n >> 1] : 0.5 * ((double)srt[(n >> 1) - 1] + (double)srt[n >> 1]);
+        double* orow = A.out + (size_t)s * A.ncols;
+
+        bool uniq_done = false; Uniq U;
+        // change_quantiles cache
+        double cq_ql = -1.0, cq_qh = -1.0; int cq_abs = -1;
+        double cq_lo = 0.0, cq_hi = 0.0, cq_mean = 0.0; int cq_cnt = 0;
+        // friedrich cache
+        int fr_r = -1; bool fr_ok = false;
+        double* coef = scr + (A.nscr - 8);
+
+        for (int j = 0; j < A.nd; ++j) {
+            const Desc d = A.descs[j];
+            double r = dnan();
+            switch (d.calc) {
+                case TSFX_MEDIAN: r = med; break;
+                case TSFX_QUANTILE: r = m_quantile_sorted(srt, n, d.p0); break;
+                case TSFX_SYMMETRY_LOOKING: r = (fabs(mean - med) < d.p0 * (vmax - vmin)) ? 1.0 : 0.0; break;
+                case TSFX_HAS_DUPLICATE:
+                case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
+                case TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS:
+                case TSFX_SUM_OF_REOCCURRING_VALUES:
+                case TSFX_SUM_OF_REOCCURRING_DATA_POINTS:
+                case TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH: {
+                    if (!uniq_done) { U = unique_pass(srt, n, lane); uniq_done = true; }
+                    switch (d.calc) {
+                        case TSFX_HAS_DUPLICATE: r = U.any_dup ? 1.0 : 0.0; break;
+                        case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
+                            r = (double)U.n_reocc_values / (double)U.n_unique; break;
+                        case TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS:
+                            r = (double)U.n_reocc_points / dn; break;
+                        case TSFX_SUM_OF_REOCCURRING_VALUES: r = U.sum_reocc_values; break;
+                        case TSFX_SUM_OF_REOCCURRING_DATA_POINTS: r = U.sum_reocc_points; break;
+                        default: r = (double)U.n_unique / dn; break;
+                    }
+                    break;
+                }
+                case TSFX_MEAN_N_ABSOLUTE_MAX: {
+                    int k = d.i0;
+                    if (n <= k) { r = dnan(); break; }
+                    double acc = 0.0;
+                    if (lane == 0) {
+                        int a = 0, b = n - 1;
+                        for (int q = 0; q < k; ++q) {
+                            float fa = fabsf(srt[a]), fb = fabsf(srt[b]);
+                            if (fa > fb) { acc += (double)fa; ++a; } else { acc += (double)fb; --b; }
+                        }
+                    }
+                    r = __shfl_sync(FULL, acc, 0) / (double)k;
+                    break;
+                }
+                case TSFX_CHANGE_QUANTILES: {
+                    if (d.p0 >= d.p1) { r = 0.0; break; }
+                    if (!(d.p0 == cq_ql && d.p1 == cq_qh)) {
+                        cq_ql = d.p0; cq_qh = d.p1; cq_abs = -1;
+                        cq_lo = m_quantile_sorted(srt, n, d.p0);
+                        cq_hi = m_quantile_sorted(srt, n, d.p1);
+                    }
+                    if (cq_abs != d.i0) {
+                        cq_abs = d.i0;
+                        int c = 0;
+                        double sm = 0.0;
+                        for (int i = lane; i + 1 < n; i += 32) {
+                            double a = (double)xs[i], b = (double)xs[i + 1];
+                            if (a >= cq_lo && a <= cq_hi && b >= cq_lo && b <= cq_hi) {
+                                double dx = b - a;
+                                if (cq_abs) dx = fabs(dx);
+                                sm += dx;
+                                ++c;
+                            }
+                        }
+                        cq_cnt = wsumi(c);
+                        cq_mean = wsum(sm) / (double)cq_cnt;
+                    }
+                    if (cq_cnt == 0) { r = 0.0; break; }
+                    if (d.attr == TSFX_AGG_MEAN) { r = cq_mean; break; }
+                    double q2 = 0.0;
+                    for (int i = lane; i + 1 < n; i += 32) {
+                        double a = (double)xs[i], b = (double)xs[i + 1];
+                        if (a >= cq_lo && a <= cq_hi && b >= cq_lo && b <= cq_hi) {
+                            double dx = b - a;
+                            if (cq_abs) dx = fabs(dx);
+                            dx -= cq_mean;
+                            q2 = fma(dx, dx, q2);
+                        }
+                    }
+                    double v = wsum(q2) / (double)cq_cnt;
+                    r = (d.attr == TSFX_AGG_STD) ? sqrt(v) : v;
+                    break;
+                }
+                case TSFX_FRIEDRICH_COEFFICIENTS:
+                case TSFX_MAX_LANGEVIN_FIXED_POINT: {
+                    if (fr_r != d.i2) {
+                        __syncwarp();
+                        fr_ok = friedrich_fit(xs, srt, n, d.i2, scr, coef, lane);
+                        fr_r = d.i2;
+                    }
+                    if (!fr_ok) { r = dnan(); break; }
+                    if (d.calc == TSFX_FRIEDRICH_COEFFICIENTS) r = (d.i0 >= 0 && d.i0 <= 3) ? coef[d.i0] : dnan();
+                    else r = m_poly3_max_real_root(coef[0], coef[1], coef[2], coef[3]);
+                    break;
+                }
+                default: break;
+            }
+            if (lane == 0) orow[d.col] = r;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_sorted(const SortedArgs& A0, int max_len, cudaStream_t st, int sm_count) {
+    SortedArgs A = A0;
+    A.npad = (max_len + 3) & ~3;
+    int p2 = 1;
+    while (p2 < max_len) p2 <<= 1;
+    A.npow2 = std::max(p2, 4);
+    A.nscr = (A.nscr + 1) & ~1;
+    size_t per = (size_t)A.nscr * 8 + (size_t)A.npad * 4 + (size_t)A.npow2 * 4;
+    per = (per + 15) & ~(size_t)15;
+    A.bytes_per_warp = (int)per;
+    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
+    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 100 * 1024 / per));
+    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
+    size_t smem = per * wpc;
+    int64_t cap = (int64_t)sm_count * 16;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
+#define TSFX_LAUNCH(W)                                                                                     \
+    {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(k_sorted<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                    \
+        k_sorted<W><<<grid, W * 32, smem, st>>>(A);                                                        \
+    }
+    switch (wpc) {
+        case 8: TSFX_LAUNCH(8) break;
+        case 4: TSFX_LAUNCH(4) break;
+        case 2: TSFX_LAUNCH(2) break;
+        default: TSFX_LAUNCH(1) break;
+    }
+#undef TSFX_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace tsfx

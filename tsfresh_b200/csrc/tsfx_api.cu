@@ -354,6 +354,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             case G_SEQ: {
                 SeqArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8);
                 e = launch_seq(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }

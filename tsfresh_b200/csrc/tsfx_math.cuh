@@ -104,7 +104,9 @@ TSFX_HD LinReg m_linregress(double n, double xmean, double ymean, double ssxm, d
     double df = n - 2.0;
     double t = r * sqrt(df / ((1.0 - r + 1e-20) * (1.0 + r + 1e-20)));
     R.pvalue = m_student_two_sided(t, df);
-    R.stderr_ = sqrt((1.0 - r * r) * ssym / ssxm / df);
+    // df == 0 (two points): r is +-1 up to rounding, so scipy's (1 - r^2) * ssym / ssxm / 0 is 0/0 = NaN
+    // or tiny/0 = inf depending on the last bit of r; the mathematically exact value is returned here.
+    R.stderr_ = (df == 0.0) ? m_nan() : sqrt((1.0 - r * r) * ssym / ssxm / df);
     return R;
 }
 
