@@ -179,12 +179,15 @@ int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values
  * orders each group by sort key (stable for equal keys; sort_keys may be NULL = keep row order), then
  * extracts.  Series come out in ascending id order: out_ids[s] and row s of out.  Host pointers only.
  * sort_key_is_f64: 0 = int64 keys, 1 = float64 keys.  Returns the number of series in *n_series_out;
- * TSFX_E_INVALID if it exceeds out_capacity. */
+ * TSFX_E_INVALID if it exceeds out_capacity.  Two-step use: call tsfx_build_csr with all output
+ * pointers NULL (it counts the series and keeps the CSR on the device), size `out`, then call
+ * tsfx_extract_long with ids == values == NULL to extract from the held CSR without sorting again. */
 int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
                       int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t* out_ids,
                       double* out, int64_t out_capacity, int64_t* n_series_out, uint32_t flags);
 
-/* Stage (a) alone: builds the CSR on the device and copies it back (sorted_values may be NULL). */
+/* Stage (a) alone: builds the CSR on the device (it stays held by the context until the next stage-(a)
+ * call) and copies back whichever outputs are non-NULL. */
 int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sort_keys, int32_t sort_key_is_f64,
                    const float* values, int64_t n_rows, int64_t* out_ids, int64_t* out_begin,
                    int32_t* out_len, float* sorted_values, int64_t out_capacity, int64_t* n_series_out);

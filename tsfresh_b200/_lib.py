@@ -158,25 +158,20 @@ class DevicePlan:
                 is_f64 = 1
             else:
                 sort_keys = np.ascontiguousarray(sort_keys, dtype=np.int64)
-        cap = len(ids)
-        out_ids = np.empty(cap, dtype=np.int64)
-        # the number of series is not known before the device pass: size for the worst case lazily
         n_series = ctypes.c_int64(0)
-        out = np.empty((0, self.n_cols))
-        # first call with capacity 0 only counts when the frame is large; small frames go straight
-        guess = cap if cap * self.n_cols <= (1 << 24) else 0
-        out = np.empty((guess, self.n_cols), dtype=np.float64)
-        rc = self.ctx.lib.tsfx_extract_long(self.ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids),
-                                            _ptr(out_ids), _ptr(out) if guess else _ptr(np.empty(1)), guess,
-                                            ctypes.byref(n_series), flags)
-        if rc == -1 and n_series.value > guess:
-            out = np.empty((n_series.value, self.n_cols), dtype=np.float64)
-            rc = self.ctx.lib.tsfx_extract_long(self.ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values),
-                                                len(ids), _ptr(out_ids), _ptr(out), n_series.value,
-                                                ctypes.byref(n_series), flags)
-        self.ctx.check(rc, "tsfx_extract_long")
+        lib, h = self.ctx.lib, self.ctx.h
+        # step 1: stage (a) on the device, count the series; step 2: size the result, extract from the held CSR
+        rc = lib.tsfx_build_csr(h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids), None, None, None, None,
+                                0, ctypes.byref(n_series))
+        self.ctx.check(rc, "tsfx_build_csr")
         k = n_series.value
-        return out_ids[:k].copy(), out[:k]
+        out_ids = np.empty(k, dtype=np.int64)
+        out = np.empty((k, self.n_cols), dtype=np.float64)
+        if k:
+            rc = lib.tsfx_extract_long(h, self.h, None, None, 0, None, len(ids), _ptr(out_ids), _ptr(out), k,
+                                       ctypes.byref(n_series), flags)
+            self.ctx.check(rc, "tsfx_extract_long")
+        return out_ids, out
 
     # ---- device-pointer entry points (torch tensors own the memory) ----------------------------
     def extract_dense_device(self, values_ptr, n_series, length, out_ptr, timing=False):

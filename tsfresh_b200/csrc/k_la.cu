@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
     double* bvec = G + pmax * pmax;                        // pmax
     double* res = bvec + pmax;                             // 8 : staged results
     int* colmap = reinterpret_cast<int*>(res + 8);         // pmax ints (pmax is even)
-    float* xs = reinterpret_cast<float*>(colmap + pmax);
+    float* xs = reinterpret_cast<float*>(colmap + ((pmax + 3) & ~3));
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
     for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
@@ -228,7 +228,7 @@ cudaError_t launch_la(const LaArgs& A0, int max_len, cudaStream_t st, int sm_cou
     A.npad = (max_len + 3) & ~3;
     int pmax = std::max(adf_maxlag(max_len) + 2, 34);       // 33 covers ar k <= 32
     pmax = (pmax + 1) & ~1;
-    size_t per = (size_t)A.npad * 16 + (size_t)pmax * pmax * 8 + (size_t)pmax * 8 + 64 + (size_t)pmax * 4 + (size_t)A.npad * 4;
+    size_t per = (size_t)A.npad * 16 + (size_t)pmax * pmax * 8 + (size_t)pmax * 8 + 64 + (size_t)((pmax + 3) & ~3) * 4 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     if (per > 227 * 1024) return cudaErrorInvalidConfiguration;

@@ -47,6 +47,7 @@ struct tsfx_ctx {
     float ms[G_COUNT];
     int launches = 0;
     CsrWorkspace csr;
+    int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
 };
 
 struct tsfx_plan {
@@ -471,9 +472,12 @@ extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sor
     if (n_rows == 0) return TSFX_OK;
     std::string msg;
     int64_t ns = 0;
+    ctx->held_series = -1;
     int rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
     if (rc) return fail(ctx, rc, msg);
+    ctx->held_series = ns;
     *n_series_out = ns;
+    if (!out_ids && !out_begin && !out_len && !sorted_values) return TSFX_OK;      // count + keep on device
     if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
     if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_begin) CK(cudaMemcpyAsync(out_begin, ctx->csr.d_begin, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -489,16 +493,26 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
     if (!ctx) return TSFX_E_INVALID;
     if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
     if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long takes host pointers");
-    if (n_rows < 0 || !n_series_out || (n_rows > 0 && (!ids || !values || !out)))
+    const bool reuse = (ids == nullptr && values == nullptr);     // run on the CSR held from tsfx_build_csr
+    if (n_rows < 0 || !n_series_out || (!reuse && n_rows > 0 && (!ids || !values)) || !out)
         return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: bad arguments");
     CK(cudaSetDevice(ctx->device));
     *n_series_out = 0;
-    if (n_rows == 0) return TSFX_OK;
     std::string msg;
     int64_t ns = 0;
-    int rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
-    if (rc) return fail(ctx, rc, msg);
+    int rc;
+    if (reuse) {
+        if (ctx->held_series < 0) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: no CSR is held by this context");
+        ns = ctx->held_series;
+    } else {
+        if (n_rows == 0) return TSFX_OK;
+        ctx->held_series = -1;
+        rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
+        if (rc) return fail(ctx, rc, msg);
+        ctx->held_series = ns;
+    }
     *n_series_out = ns;
+    if (ns == 0) return TSFX_OK;
     if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
     int max_len = 0;
     if (csr_max_len(ctx->csr, ctx->csr.d_len, ns, ctx->stream, &max_len)) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");

@@ -69,7 +69,7 @@ __device__ __forceinline__ int load_series(const SeriesRef& R, int64_t s, float*
     int n;
     if (R.begin) { b = R.begin[s]; n = R.len[s]; } else { b = s * (int64_t)R.dense_len; n = R.dense_len; }
     const float* src = R.values + b;
-    if ((((uintptr_t)src) & 15u) == 0) {
+    if (((((uintptr_t)src) | ((uintptr_t)xs)) & 15u) == 0) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         int n4 = n >> 2;
         for (int i = lane; i < n4; i += 32) {

@@ -1,0 +1,58 @@
+"""The reference's plugin seam #1 (tsfresh/utilities/distribution.py:64-105): a Distributor whose
+`map_reduce` evaluates the whole `data` object on the GPU instead of mapping a Python function over chunks.
+
+    from tsfresh import extract_features                 # the unmodified reference driver
+    from tsfresh_b200.distributor import B200Distributor
+    X = extract_features(df, column_id="id", column_sort="time", distributor=B200Distributor())
+
+`extract_features` calls `distributor.map_reduce(_do_extraction_on_chunk, data=<TsData>, chunk_size=...,
+function_kwargs={default_fc_parameters, kind_to_fc_parameters, show_warnings})` (extraction.py:288-299) and
+pivots the returned (id, name, value) triples (data.py:86-121).  The Python `map_function` is never called.
+"""
+import numpy as np
+
+from .plan import Plan
+
+
+def _reference_base():
+    try:
+        from tsfresh.utilities.distribution import DistributorBaseClass
+        return DistributorBaseClass
+    except Exception:
+        return object
+
+
+def is_distributor(obj):
+    base = _reference_base()
+    return (base is not object and isinstance(obj, base)) or hasattr(obj, "map_reduce")
+
+
+class B200Distributor(_reference_base()):
+    def __init__(self, device=None):
+        self.device = device
+
+    def map_reduce(self, map_function, data, function_kwargs=None, chunk_size=None, data_length=None):
+        from .extraction import _device_plan, get_context
+        kw = function_kwargs or {}
+        default = kw.get("default_fc_parameters") or {}
+        per_kind = kw.get("kind_to_fc_parameters") or {}
+        ctx = get_context(self.device)
+        by_kind = {}
+        for sid, kind, series in data:              # the adapter already grouped by (id, kind) and sorted by time
+            by_kind.setdefault(str(kind), []).append((sid, np.asarray(series, dtype=np.float32)))
+        triples = []
+        for kind, items in by_kind.items():
+            plan = Plan(per_kind.get(kind, default))
+            if plan.n_cols == 0:
+                continue
+            dp = _device_plan(ctx, plan)
+            lens = np.array([len(v) for _, v in items], dtype=np.int32)
+            begin = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+            mat = dp.extract_csr(np.concatenate([v for _, v in items]), begin, lens)
+            names = [kind + "__" + s for s in plan.suffixes]
+            for r, (sid, _) in enumerate(items):
+                triples.extend((sid, n, mat[r, c]) for c, n in enumerate(names))
+        return triples
+
+    def close(self):
+        pass

@@ -1,0 +1,228 @@
+"""extract_features(): the drop-in host side of the hot path.
+
+Mirrors the reference driver (tsfresh/feature_extraction/extraction.py:30-305) and its input adapters
+(tsfresh/feature_extraction/data.py:124-338, 447-500): same signature, same validation errors, same
+column names / order / index.  Everything between "a long (id, sort, value) frame" and "the dense
+[n_ids x n_features] float64 matrix" happens on the GPU behind the C ABI (include/tsfx.h):
+group-by-id + sort-by-time -> CSR (tsfx_extract_long), then the fused per-series kernels.
+
+Differences that are part of the contract (BASELINE.json north_star):
+  * values are ingested as float32 (arithmetic is float64); parity with the reference is defined on
+    float32-representable inputs;
+  * there is no CPU fallback: a calculator or parameter without a GPU implementation raises
+    NotImplementedError, a missing library or device raises RuntimeError;
+  * n_jobs / chunksize / distributor / profile* are accepted for signature compatibility; work always
+    runs on this process's CUDA device (one process per GPU, see tsfresh_b200.distributed).
+"""
+import threading
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .plan import Plan
+from .settings import ComprehensiveFCParameters
+
+_ctx_lock = threading.Lock()
+_contexts = {}
+
+
+def get_context(device=None):
+    """The process-wide tsfx context for `device` (default: LOCAL_RANK or 0)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _ctx_lock:
+        if device not in _contexts:
+            _contexts[device] = _lib.Context(device)
+        return _contexts[device]
+
+
+def _device_plan(ctx, plan):
+    key = plan.descs.tobytes() + repr(plan.cwt_scales).encode()
+    dp = ctx._plans.get(key)
+    if dp is None:
+        dp = _lib.DevicePlan(ctx, plan)
+        ctx._plans[key] = dp
+    return dp
+
+
+# ------------------------------------------------------------------ validation (data.py:124-167)
+def _check_colname(*columns):
+    for col in columns:
+        if str(col).endswith("_"):
+            raise ValueError("Dict keys are not allowed to end with '_': {}".format(col))
+        if "__" in str(col):
+            raise ValueError("Dict keys are not allowed to contain '__': {}".format(col))
+
+
+def _check_nan(df, *columns):
+    for col in columns:
+        if col not in df.columns:
+            raise ValueError("Column not found: {}".format(col))
+        if df[col].isnull().any():
+            raise ValueError("Column must not contain NaN values: {}".format(col))
+
+
+def _value_columns(df, *other):
+    cols = [c for c in df.columns if c not in other]
+    if len(cols) == 0:
+        raise ValueError("Could not guess the value column! Please hand it to the function as an argument.")
+    return cols
+
+
+def _sort_keys(col):
+    """Sort column -> int64 or float64 keys whose order equals the column's order."""
+    if col is None:
+        return None
+    a = col.to_numpy()
+    if a.dtype.kind in "iub":
+        return a.astype(np.int64, copy=False)
+    if a.dtype.kind == "f":
+        return a.astype(np.float64, copy=False)
+    if a.dtype.kind in "mM":
+        return a.view(np.int64)
+    _, inv = np.unique(a, return_inverse=True)      # strings / objects: order-preserving ranks
+    return inv.astype(np.int64)
+
+
+def _frames(container, column_id, column_kind, column_value, column_sort):
+    """Normalises the supported input formats (data.py:447-500) to a list of
+    (kind, id column, sort keys or None, float32 values, has_datetime_index)."""
+    out = []
+    if isinstance(container, pd.DataFrame):
+        df = container
+        if column_id is None:
+            raise ValueError("A value for column_id needs to be supplied")
+        if column_kind is not None:                                  # long format (data.py:233-291)
+            if column_value is None:
+                poss = _value_columns(df, column_id, column_sort, column_kind)
+                if len(poss) != 1:
+                    raise ValueError(
+                        "Could not guess the value column, as the number of unused columns os not equal to 1."
+                        f"These columns where currently unused: {','.join(poss)}"
+                        "Please hand it to the function as an argument.")
+                column_value = poss[0]
+            _check_nan(df, column_id, column_kind, column_value)
+            if column_sort is not None:
+                _check_nan(df, column_sort)
+            for kind, sub in df.groupby(column_kind, sort=True):
+                out.append((str(kind), sub[column_id], sub[column_sort] if column_sort is not None else None,
+                            sub[column_value], isinstance(sub.index, pd.DatetimeIndex)))
+            id_dtype = df[column_id].dtype
+        else:                                                        # wide format (data.py:181-230)
+            _check_nan(df, column_id)
+            value_columns = [column_value] if column_value is not None else _value_columns(df, column_id, column_sort)
+            _check_nan(df, *value_columns)
+            _check_colname(*value_columns)
+            if column_sort is not None:
+                _check_nan(df, column_sort)
+            for kind in value_columns:
+                out.append((str(kind), df[column_id], df[column_sort] if column_sort is not None else None, df[kind],
+                            isinstance(df.index, pd.DatetimeIndex)))
+            id_dtype = df[column_id].dtype
+    elif isinstance(container, dict):                                # dict of frames (data.py:294-338)
+        _check_colname(*list(container.keys()))
+        id_dtype = None
+        for df in container.values():
+            _check_nan(df, column_id, column_value)
+        for kind, df in container.items():
+            if column_sort is not None:
+                _check_nan(df, column_sort)
+            out.append((str(kind), df[column_id], df[column_sort] if column_sort is not None else None,
+                        df[column_value], isinstance(df.index, pd.DatetimeIndex)))
+            id_dtype = df[column_id].dtype
+    else:
+        raise ValueError("df must be a DataFrame or a dict of DataFrames. "
+                         "See https://tsfresh.readthedocs.io/en/latest/text/data_formats.html")
+    return out, id_dtype
+
+
+def _encode_ids(id_series_list):
+    """ids of all kinds -> int64 codes that sort like the ids, plus the decoder array (or None)."""
+    first = id_series_list[0].to_numpy()
+    if all(s.to_numpy().dtype.kind in "iu" for s in id_series_list):
+        return [s.to_numpy().astype(np.int64, copy=False) for s in id_series_list], None
+    allv = np.concatenate([s.to_numpy() for s in id_series_list]) if len(id_series_list) > 1 else first
+    uniq, inv = np.unique(allv, return_inverse=True)
+    codes, pos = [], 0
+    for s in id_series_list:
+        codes.append(inv[pos:pos + len(s)].astype(np.int64))
+        pos += len(s)
+    return codes, uniq
+
+
+def extract_features(timeseries_container, default_fc_parameters=None, kind_to_fc_parameters=None, column_id=None,
+                     column_sort=None, column_kind=None, column_value=None, chunksize=None, n_jobs=1,
+                     show_warnings=False, disable_progressbar=False, impute_function=None, profile=False,
+                     profiling_filename="profile.txt", profiling_sorting="cumulative", distributor=None, pivot=True,
+                     device=None):
+    """GPU implementation of tsfresh.extract_features (extraction.py:30-190).  Returns the same
+    pandas.DataFrame (float64, index = sorted ids, columns `{kind}__{calculator}[__{params}]`), or the
+    list of (id, name, value) triples when pivot=False."""
+    if default_fc_parameters is None and kind_to_fc_parameters is None:
+        default_fc_parameters = ComprehensiveFCParameters()
+    elif default_fc_parameters is None and kind_to_fc_parameters is not None:
+        default_fc_parameters = {}
+    if distributor is not None:
+        from .distributor import is_distributor
+        if not is_distributor(distributor):
+            raise ValueError("the passed distributor is not an DistributorBaseClass object")
+
+    frames, id_dtype = _frames(timeseries_container, column_id, column_kind, column_value, column_sort)
+    ctx = get_context(device)
+    codes, decoder = _encode_ids([f[1] for f in frames])
+
+    blocks = []           # (column names, ids (codes), matrix)
+    for (kind, _ids, sort_col, values, has_dt), id_codes in zip(frames, codes):
+        if kind_to_fc_parameters and kind in kind_to_fc_parameters:
+            fc = kind_to_fc_parameters[kind]
+        else:
+            fc = default_fc_parameters
+        plan = Plan(fc, has_datetime_index=has_dt)
+        for name in plan.skipped:
+            if show_warnings:
+                warnings.warn("{} requires the data to have a index of type {}. Results will "
+                              "not be calculated".format(name, pd.DatetimeIndex))
+        names = [kind + "__" + s for s in plan.suffixes]
+        if plan.n_cols == 0 or len(id_codes) == 0:
+            uid = np.unique(id_codes)
+            blocks.append((names, uid, np.empty((len(uid), 0))))
+            continue
+        dp = _device_plan(ctx, plan)
+        v32 = values.to_numpy().astype(np.float32, copy=False)
+        uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32)
+        blocks.append((names, uid, mat))
+
+    # ---- assemble (PartitionedTsData.pivot, data.py:86-121): union of ids, sorted, id dtype restored
+    all_ids = blocks[0][1] if len(blocks) == 1 else np.unique(np.concatenate([b[1] for b in blocks]))
+    index = all_ids if decoder is None else decoder[all_ids]
+    if not pivot:
+        triples = []
+        for names, uid, mat in blocks:
+            ids_out = uid if decoder is None else decoder[uid]
+            for r, i in enumerate(ids_out):
+                triples.extend((i, n, mat[r, c]) for c, n in enumerate(names))
+        return triples
+    if len(blocks) == 1:
+        data = blocks[0][2]
+        columns = blocks[0][0]
+    else:
+        columns = [n for b in blocks for n in b[0]]
+        data = np.full((len(all_ids), len(columns)), np.nan)
+        c0 = 0
+        for names, uid, mat in blocks:
+            rows = np.searchsorted(all_ids, uid)
+            data[rows, c0:c0 + len(names)] = mat
+            c0 += len(names)
+    result = pd.DataFrame(data, index=pd.Index(index), columns=columns, dtype=float)
+    if id_dtype is not None:
+        try:
+            result.index = result.index.astype(id_dtype)
+        except (TypeError, ValueError):
+            pass
+    result = result.sort_index()
+    if impute_function is not None:
+        impute_function(result)
+    return result
