@@ -117,12 +117,13 @@ def cpu_baseline(length, name, target_seconds, cores=None):
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        # calibrate on one series per core, then size the sample for ~target_seconds
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(1000 + i, 1, length, name) for i in range(cores)])
-        per_series = max(time.perf_counter() - t0, 1e-3)
-        per_core = max(1, int(target_seconds / per_series))
-        per_core = min(per_core, 64)
+        # warm the workers (imports), calibrate on two series per core using the in-worker time, then size the
+        # sample for ~target_seconds of wall clock
+        pool.map(_cpu_worker, [(900 + i, 1, length, name) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(1000 + i, 2, length, name) for i in range(cores)])
+        per_series = max(float(np.median([r[1] for r in res])) / 2.0, 1e-4)
+        per_core = max(2, int(target_seconds / per_series))
+        per_core = min(per_core, 2000)
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(2000 + i, per_core, length, name) for i in range(cores)])
         wall = time.perf_counter() - t0
@@ -195,7 +196,10 @@ def main():
     S, L = args.series, args.len
     plan = Plan(settings_by_name(args.settings))
     F = plan.n_cols
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream shared with the library, so torch's CUDA events bracket the library's launches
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
     dp = _lib.DevicePlan(ctx, plan)
 

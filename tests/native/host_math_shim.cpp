@@ -12,7 +12,7 @@ void hm_levinson(const double* acv, int nlags, double* out, double* work) { m_le
 double hm_quantile(const double* s, int n, double q) { return m_quantile_sorted(s, n, q); }
 void hm_linreg(double n, double xm, double ym, double sxx, double syy, double sxy, double* o) {
     LinReg r = m_linregress(n, xm, ym, sxx, syy, sxy);
-    o[0] = r.pvalue; o[1] = r.rvalue; o[2] = r.intercept; o[3] = r.slope; o[4] = r.stderr_;
+    o[0] = m_linreg_pick(r, 0); o[1] = r.rvalue; o[2] = r.intercept; o[3] = r.slope; o[4] = r.stderr_;
 }
 int hm_cholesky_solve(double* A, int n, double* b) {
     if (!m_cholesky(A, n, n)) return 0;

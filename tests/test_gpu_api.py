@@ -1,0 +1,112 @@
+"""extract_features() drop-in behaviour on the GPU path: input formats, row-order invariance (device sort),
+id dtypes, kind handling, column names -- mirrors tests/units/feature_extraction/test_extraction.py and
+test_data.py of the reference."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle.extract import compare, oracle_rows
+from tests.helpers import synthetic_series
+from tsfresh_b200 import EfficientFCParameters, MinimalFCParameters, extract_features
+from tsfresh_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+
+def long_frame(series, ids=None, shuffle_seed=None):
+    ids = list(range(len(series))) if ids is None else ids
+    df = pd.DataFrame({
+        "id": np.concatenate([np.full(len(s), i) for i, s in zip(ids, series)]),
+        "time": np.concatenate([np.arange(len(s)) for s in series]),
+        "value": np.concatenate(series).astype(np.float32),
+    })
+    if shuffle_seed is not None:
+        df = df.sample(frac=1.0, random_state=shuffle_seed).reset_index(drop=True)
+    return df
+
+
+def check(X, series, settings, prefix="value__"):
+    plan = Plan(settings)
+    assert list(X.columns) == [prefix + s for s in plan.suffixes]
+    want = oracle_rows([np.asarray(s, np.float32).astype(np.float64) for s in series], settings)
+    bad = compare(X.to_numpy(), want, plan.suffixes)
+    assert not bad, bad[:20]
+
+
+def test_long_frame_sorted_and_shuffled():
+    rng = np.random.default_rng(0)
+    series = [rng.standard_normal(n).astype(np.float32) for n in (50, 256, 17, 300, 64, 1, 2)]
+    s = EfficientFCParameters()
+    X = extract_features(long_frame(series), column_id="id", column_sort="time", default_fc_parameters=s)
+    assert X.index.tolist() == list(range(len(series))) and X.dtypes.eq(np.float64).all()
+    check(X, series, s)
+    Xs = extract_features(long_frame(series, shuffle_seed=3), column_id="id", column_sort="time", default_fc_parameters=s)
+    np.testing.assert_array_equal(X.to_numpy(), Xs.to_numpy())       # test_extraction.py:207-237
+    assert list(X.columns) == list(Xs.columns)
+
+
+def test_ids_unsorted_negative_and_strings():
+    series = list(synthetic_series(1, 5, 40))
+    s = MinimalFCParameters()
+    X = extract_features(long_frame(series, ids=[30, -2, 7, 100, 0], shuffle_seed=1), column_id="id", column_sort="time",
+                         default_fc_parameters=s)
+    assert X.index.tolist() == [-2, 0, 7, 30, 100]
+    order = [1, 4, 2, 0, 3]
+    check(X, [series[i] for i in order], s)
+    df = long_frame(series, ids=["b", "a", "e", "d", "c"])
+    X2 = extract_features(df, column_id="id", column_sort="time", default_fc_parameters=s)
+    assert X2.index.tolist() == ["a", "b", "c", "d", "e"]
+    check(X2, [series[i] for i in [1, 0, 4, 3, 2]], s)
+
+
+def test_wide_dict_and_kind_formats():
+    a = list(synthetic_series(2, 4, 30))
+    b = list(synthetic_series(3, 4, 30))
+    s = MinimalFCParameters()
+    wide = pd.DataFrame({"id": np.repeat(np.arange(4), 30), "t": np.tile(np.arange(30), 4),
+                         "a": np.concatenate(a), "b": np.concatenate(b)})
+    X = extract_features(wide, column_id="id", column_sort="t", default_fc_parameters=s)
+    assert X.shape == (4, 20)
+    check(X[[c for c in X.columns if c.startswith("a__")]], a, s, "a__")
+    check(X[[c for c in X.columns if c.startswith("b__")]], b, s, "b__")
+    long = wide.melt(id_vars=["id", "t"], var_name="kind", value_name="val")
+    Xl = extract_features(long, column_id="id", column_sort="t", column_kind="kind", column_value="val", default_fc_parameters=s)
+    pd.testing.assert_frame_equal(X, Xl[X.columns])
+    d = {"a": wide[["id", "t", "a"]].rename(columns={"a": "v"}), "b": wide[["id", "t", "b"]].rename(columns={"b": "v"})}
+    Xd = extract_features(d, column_id="id", column_sort="t", column_value="v", default_fc_parameters=s)
+    pd.testing.assert_frame_equal(X, Xd[X.columns])
+    # per-kind settings (extraction.py:333-336, test_extraction.py:78-89)
+    Xk = extract_features(wide, column_id="id", column_sort="t", default_fc_parameters=s,
+                          kind_to_fc_parameters={"b": {"maximum": None, "quantile": [{"q": 0.5}]}})
+    assert [c for c in Xk.columns if c.startswith("b__")] == ["b__maximum", "b__quantile__q_0.5"]
+
+
+def test_errors_like_the_reference():
+    df = long_frame(list(synthetic_series(1, 3, 10)))
+    with pytest.raises(ValueError):
+        extract_features(df, column_id=None, column_sort="time")
+    bad = df.copy()
+    bad.loc[3, "value"] = np.nan
+    with pytest.raises(ValueError, match="must not contain NaN"):
+        extract_features(bad, column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters())
+    with pytest.raises(ValueError, match="not allowed to contain '__'"):
+        extract_features(df.rename(columns={"value": "va__lue"}), column_id="id", column_sort="time",
+                         default_fc_parameters=MinimalFCParameters())
+    with pytest.raises(NotImplementedError):          # no CPU fallback for user callables
+        extract_features(df, column_id="id", column_sort="time", default_fc_parameters={(lambda x: 1.0): None})
+    with pytest.raises(ValueError):
+        extract_features([1, 2, 3], column_id="id")
+
+
+def test_pivot_false_triples():
+    series = list(synthetic_series(5, 3, 20))
+    tr = extract_features(long_frame(series), column_id="id", column_sort="time",
+                          default_fc_parameters={"maximum": None, "length": None}, pivot=False)
+    assert len(tr) == 6 and tr[0][1] == "value__maximum" and tr[1] == (0, "value__length", 20.0)
+
+
+def test_duplicate_timestamps_are_stable():
+    # equal sort keys keep their row order (documented tie rule; the reference's quicksort leaves it unspecified)
+    df = pd.DataFrame({"id": [1, 1, 1, 0, 0], "time": [5, 5, 1, 2, 2], "value": np.float32([3, 4, 9, 7, 8])})
+    X = extract_features(df, column_id="id", column_sort="time", default_fc_parameters={"mean_change": None})
+    assert X.loc[1, "value__mean_change"] == (4 - 9) / 2 and X.loc[0, "value__mean_change"] == 1.0

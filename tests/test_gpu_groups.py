@@ -64,7 +64,9 @@ def test_group_short_and_ragged(ctx, group):
     #    statistic of order 1e16, the GPU path returns NaN (Cholesky on the normal equations);
     #  * the Friedrich cubic has noise coefficients (1e-17) whose roots are arbitrary.
     # Those two groups are therefore checked without the two collinear series.
-    series = short_and_ragged(degenerate=group not in ("la", "sorted"))
+    #  * the Welch spectrum of the alternating series is one spike plus rounding noise; binning the noise
+    #    (fourier_entropy) is not reproducible.
+    series = short_and_ragged(degenerate=group not in ("la", "sorted", "spectral"))
     bad, *_ = gpu_vs_oracle(ctx, settings_of(GROUPS[group]), series)
     assert not bad, _report(bad)
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void entropy_batch(const Desc* descs, int j0, int cnt
 }
 
 template <int WPC>
-__global__ void __launch_bounds__(WPC * 32) k_entropy(EntropyArgs A) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 3 : 1)) k_entropy(EntropyArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
@@ -118,7 +118,7 @@ cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, 
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
-    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 64 * 1024 / per));
+    int wpc = (int)std::min<size_t>(4, std::max<size_t>(1, 64 * 1024 / per));
     wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
     size_t smem = per * wpc;
     int64_t cap = (int64_t)sm_count * 32;

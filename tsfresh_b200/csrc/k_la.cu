@@ -62,6 +62,47 @@ __device__ __forceinline__ void adf_gram(const int* colmap, int q, int t0, int t
     __syncwarp();
 }
 
+// ---- warp-cooperative dense SPD kernels (row-major lower triangle in shared memory) -----------------
+// In-place Cholesky; returns the number of columns factorised before a non-positive pivot (q if none).
+__device__ __forceinline__ int warp_cholesky(double* G, int q, int lda, int lane) {
+    for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        for (int k = lane; k < j; k += 32) { double v = G[j * lda + k]; s = fma(v, v, s); }
+        double d = G[j * lda + j] - wsum(s);
+        if (!(d > 0.0)) return j;
+        d = sqrt(d);
+        __syncwarp();
+        if (lane == 0) G[j * lda + j] = d;
+        for (int i = j + 1 + lane; i < q; i += 32) {
+            double t = G[i * lda + j];
+            for (int k = 0; k < j; ++k) t = fma(-G[i * lda + k], G[j * lda + k], t);
+            G[i * lda + j] = t / d;
+        }
+        __syncwarp();
+    }
+    return q;
+}
+// L z = b in place (column oriented: after z_k is known every lane retires it from its own row)
+__device__ __forceinline__ void warp_forward(const double* L, int q, int lda, double* b, int lane) {
+    for (int k = 0; k < q; ++k) {
+        double zk = b[k] / L[k * lda + k];
+        __syncwarp();
+        if (lane == 0) b[k] = zk;
+        for (int i = k + 1 + lane; i < q; i += 32) b[i] = fma(-L[i * lda + k], zk, b[i]);
+        __syncwarp();
+    }
+}
+// L^T x = z in place
+__device__ __forceinline__ void warp_backward(const double* L, int q, int lda, double* b, int lane) {
+    for (int i = q - 1; i >= 0; --i) {
+        double xi = b[i] / L[i * lda + i];
+        __syncwarp();
+        if (lane == 0) b[i] = xi;
+        for (int k = lane; k < i; k += 32) b[k] = fma(-L[i * lda + k], xi, b[k]);
+        __syncwarp();
+    }
+}
+
 template <int WPC>
 __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -117,24 +158,21 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                         }
                         __syncwarp();
                         int good = 0;
-                        if (lane == 0) {
-                            if (M.vmax == M.vmin) {
-                                // rank-one design (constant series): numpy pinv's minimum-norm solution
-                                double cst = M.vmin, sc = cst / (1.0 + (double)k * cst * cst);
-                                bvec[0] = sc;
-                                for (int a = 1; a < q; ++a) bvec[a] = sc * cst;
-                                good = 2;
-                            } else if (m_cholesky(G, q, q)) {
-                                m_forward(G, q, q, bvec);
-                                m_backward(G, q, q, bvec);
-                                // undo the centring: const = c~ + mean * (1 - sum phi)
-                                double sphi = 0.0;
-                                for (int a = 1; a < q; ++a) sphi += bvec[a];
-                                bvec[0] = bvec[0] + M.mean * (1.0 - sphi);
-                                good = 1;
-                            }
+                        if (M.vmax == M.vmin) {
+                            // rank-one design (constant series): numpy pinv's minimum-norm solution
+                            double cst = M.vmin, sc = cst / (1.0 + (double)k * cst * cst);
+                            for (int a = lane; a < q; a += 32) bvec[a] = (a == 0) ? sc : sc * cst;
+                            good = 2;
+                        } else if (warp_cholesky(G, q, q, lane) == q) {
+                            warp_forward(G, q, q, bvec, lane);
+                            warp_backward(G, q, q, bvec, lane);
+                            // undo the centring: const = c~ + mean * (1 - sum phi)
+                            double sphi = 0.0;
+                            for (int a = 1 + lane; a < q; a += 32) sphi += bvec[a];
+                            sphi = wsum(sphi);
+                            if (lane == 0) bvec[0] = bvec[0] + M.mean * (1.0 - sphi);
+                            good = 1;
                         }
-                        good = __shfl_sync(FULL, good, 0);
                         __syncwarp();
                         if (!good) { ar_ok = true; for (int a = lane; a <= k; a += 32) bvec[a] = dnan(); __syncwarp(); }
                     }
@@ -156,32 +194,20 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                             double* yy = res + 7;
                             adf_gram(nullptr, p, t0, nd_, xc, dx, G, bvec, yy, lane);
                             int best_q = 2;
-                            if (lane == 0) {
-                                int okq = p;
-                                // factorise as far as the pivots stay positive (nested models)
-                                for (int jx = 0; jx < p; ++jx) {
-                                    double dg = G[jx * p + jx];
-                                    for (int kk = 0; kk < jx; ++kk) dg -= G[jx * p + kk] * G[jx * p + kk];
-                                    if (!(dg > 0.0)) { okq = jx; break; }
-                                    dg = sqrt(dg);
-                                    G[jx * p + jx] = dg;
-                                    for (int i = jx + 1; i < p; ++i) {
-                                        double sv = G[i * p + jx];
-                                        for (int kk = 0; kk < jx; ++kk) sv -= G[i * p + kk] * G[jx * p + kk];
-                                        G[i * p + jx] = sv / dg;
-                                    }
-                                }
+                            {
+                                // factorise as far as the pivots stay positive (the models are nested)
+                                const int okq = warp_cholesky(G, p, p, lane);
                                 double ssr = *yy, best_ic = 0.0;
                                 bool have = false;
+                                const double dnobs = (double)nobs;
                                 for (int i = 0; i < okq; ++i) {
-                                    double z = bvec[i];
-                                    for (int kk = 0; kk < i; ++kk) z -= G[i * p + kk] * bvec[kk];
-                                    z /= G[i * p + i];
-                                    bvec[i] = z;
+                                    double z = bvec[i] / G[i * p + i];
+                                    __syncwarp();
+                                    for (int r2 = i + 1 + lane; r2 < okq; r2 += 32) bvec[r2] = fma(-G[r2 * p + i], z, bvec[r2]);
+                                    __syncwarp();
                                     ssr -= z * z;
-                                    int q = i + 1;
+                                    const int q = i + 1;
                                     if (q >= 2) {
-                                        double dnobs = (double)nobs;
                                         double llf = -dnobs / 2.0 * log(2.0 * 3.14159265358979323846) -
                                                      dnobs / 2.0 * log(ssr / dnobs) - dnobs / 2.0;
                                         double pen = (adf_mode == TSFX_AUTOLAG_AIC) ? 2.0 * (double)q : log(dnobs) * (double)q;
@@ -200,18 +226,18 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                         __syncwarp();
                         double* yy = res + 7;
                         adf_gram(colmap, q, t0, nd_, xc, dx, G, bvec, yy, lane);
-                        if (lane == 0) {
-                            if (m_cholesky(G, q, q)) {
-                                m_forward(G, q, q, bvec);
-                                double ssr = *yy;
-                                for (int i = 0; i < q; ++i) ssr -= bvec[i] * bvec[i];
-                                double s2 = ssr / (double)(nobs - q);
-                                stat = bvec[q - 1] / sqrt(s2);
-                                pval = m_mackinnon_p_c(stat);
-                                ulag = (double)used;
-                            }
-                            res[0] = stat; res[1] = pval; res[2] = ulag;
+                        if (warp_cholesky(G, q, q, lane) == q) {
+                            warp_forward(G, q, q, bvec, lane);
+                            double ssr = 0.0;
+                            for (int i = lane; i < q; i += 32) ssr = fma(bvec[i], bvec[i], ssr);
+                            ssr = *yy - wsum(ssr);
+                            double s2 = ssr / (double)(nobs - q);
+                            stat = bvec[q - 1] / sqrt(s2);
+                            pval = m_mackinnon_p_c(stat);
+                            ulag = (double)used;
                         }
+                        __syncwarp();
+                        if (lane == 0) { res[0] = stat; res[1] = pval; res[2] = ulag; }
                     } else if (lane == 0) { res[0] = stat; res[1] = pval; res[2] = ulag; }
                     __syncwarp();
                 }

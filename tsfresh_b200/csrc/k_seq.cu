@@ -19,7 +19,7 @@ namespace tsfx {
 
 struct SeqLayout {
     int npad, npow2, nwords, lz_lanes, cwt_n;
-    int off_tmp, off_hw, off_codes, off_trie, off_bits, off_lines, off_map, off_xs;   // byte offsets
+    int off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs;   // byte offsets
 };
 
 // ---------------------------------------------------------------------------- Lempel-Ziv
@@ -85,19 +85,21 @@ __device__ __forceinline__ void ricker_fill(double* hw, int npts, int w, int lan
     __syncwarp();
 }
 
-// scipy.stats.scoreatpercentile(window, 10) with the window copied into `buf` (<= wlen values), one lane
-__device__ __forceinline__ double percentile10(double* buf, int wlen) {
-    for (int a = 1; a < wlen; ++a) {           // insertion sort
-        double v = buf[a];
-        int b = a - 1;
-        while (b >= 0 && buf[b] > v) { buf[b + 1] = buf[b]; --b; }
-        buf[b + 1] = v;
-    }
+// scipy.stats.scoreatpercentile(win[0..wlen), 10) by rank selection (no scratch, read-only window)
+__device__ __forceinline__ double percentile10(const double* win, int wlen) {
     double idx = 10.0 / 100.0 * (double)(wlen - 1);
     int i = (int)idx;
-    if ((double)i == idx) return buf[i];
+    double v0 = 0.0, v1 = 0.0;
+    for (int a = 0; a < wlen; ++a) {
+        double va = win[a];
+        int rk = 0;
+        for (int b = 0; b < wlen; ++b) { double vb = win[b]; rk += (vb < va) || (vb == va && b < a); }
+        if (rk == i) v0 = va;
+        if (rk == i + 1) v1 = va;
+    }
+    if ((double)i == idx) return v0;
     double w0 = (double)(i + 1) - idx, w1 = idx - (double)i;
-    return (buf[i] * w0 + buf[i + 1] * w1) / (w0 + w1);
+    return (v0 * w0 + v1 * w1) / (w0 + w1);
 }
 
 template <int WPC>
@@ -105,9 +107,10 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
-    double* row0 = reinterpret_cast<double*>(base);
-    double* tmp = reinterpret_cast<double*>(base + Y.off_tmp);
+    double* rows = reinterpret_cast<double*>(base);                       // cwt_n x npad
+    double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad
     double* hw = reinterpret_cast<double*>(base + Y.off_hw);
+    unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
     unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
@@ -132,17 +135,23 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                 // up to lz_lanes consecutive LZ descriptors, one per lane
                 int cnt = 0;
                 while (j + cnt < A.nd && cnt < Y.lz_lanes && A.descs[j + cnt].calc == TSFX_LEMPEL_ZIV_COMPLEXITY) ++cnt;
+                for (int q = 0; q < cnt; ++q) {                      // symbols of every position, all lanes
+                    const int bins = A.descs[j + q].i0;
+                    const double step = __ddiv_rn(__dsub_rn(vmax, vmin), (double)bins);
+                    unsigned short* sb = symbuf + (size_t)q * Y.npad;
+                    for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                }
+                __syncwarp();
                 if (lane < cnt) {
                     const Desc d = A.descs[j + lane];
-                    const int bins = d.i0;
-                    const double step = __ddiv_rn(__dsub_rn(vmax, vmin), (double)bins);
+                    const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
                     unsigned short* first = trie + (size_t)lane * 3 * (Y.npad + 1);
                     unsigned short* next = first + (Y.npad + 1);
                     unsigned short* sym = next + (Y.npad + 1);
                     int nodes = 1, node = 0, phrases = 0;
                     first[0] = 0;                                   // 0 = no child (root is node 0)
                     for (int pos = 0; pos < n; ++pos) {
-                        int sy = lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                        int sy = sb[pos];
                         int ch = first[node];
                         while (ch != 0 && sym[ch] != sy) ch = next[ch];
                         if (ch != 0) node = ch;
@@ -202,11 +211,11 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                 ++j;
             } else if (d0.calc == TSFX_NUMBER_CWT_PEAKS) {
                 if (!cwt_ready) {
-                    // all rows 1..cwt_n once: local-maximum bit masks per row, row of width 1 kept in row0
+                    // all rows 1..cwt_n once (kept in shared memory) + local-maximum bit masks per row
                     for (int w = 1; w <= Y.cwt_n; ++w) {
                         const int npts = min(10 * w, n);
                         ricker_fill(hw, npts, w, lane);
-                        double* dst = (w == 1) ? row0 : tmp;
+                        double* dst = rows + (size_t)(w - 1) * Y.npad;
                         for (int i = lane; i < n; i += 32) dst[i] = cwt_value(xs, n, hw, npts, i);
                         __syncwarp();
                         unsigned* bits = maxbits + (size_t)(w - 1) * Y.nwords;
@@ -223,70 +232,65 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                         }
                         __syncwarp();
                     }
+                    // noise floor of _filter_ridge_lines for every column: 10th percentile of row 0 in a window
+                    {
+                        const int window = (n + 19) / 20, hf = window / 2, odd = window & 1;
+                        for (int c = lane; c < n; c += 32) {
+                            const int ws = max(c - hf, 0), we = min(c + hf + odd, n);
+                            noise[c] = percentile10(rows + ws, we - ws);
+                        }
+                        __syncwarp();
+                    }
                     cwt_ready = true;
                 }
                 const int nrows = d0.i0;
-                int result = 0;
+                short* l_last = lines;                 // last attached column
+                short* l_gap = lines + LCAP;
+                short* l_len = lines + 2 * LCAP;
+                short* l_minrow = lines + 3 * LCAP;    // smallest row so far
+                short* l_mincol = lines + 4 * LCAP;    // first column attached at that row
+                const int min_length = (nrows + 3) / 4;                       // ceil(nrows / 4)
+                // evaluates the filter of _filter_ridge_lines for one finished line
+                auto accept = [&](int li) -> bool {
+                    if (l_len[li] < min_length) return false;
+                    const int rr = l_minrow[li], cc = l_mincol[li];
+                    const double snr = fabs(rows[(size_t)rr * Y.npad + cc] / noise[cc]);
+                    return !(snr < 1.0);
+                };
+                int result = 0, nl = 0, start = -1;
                 if (lane == 0) {
-                    short* l_last = lines;                 // last attached column
-                    short* l_gap = lines + LCAP;
-                    short* l_len = lines + 2 * LCAP;
-                    short* l_minrow = lines + 3 * LCAP;    // smallest row so far
-                    short* l_mincol = lines + 4 * LCAP;    // first column attached at that row
-                    const int min_length = (nrows + 3) / 4;                       // ceil(nrows / 4)
-                    const int window = (n + 19) / 20;                             // ceil(n / 20)
-                    const int hf = window / 2, odd = window & 1;
-                    int nl = 0;
-                    // evaluates the filter of _filter_ridge_lines for one finished line
-                    auto accept = [&](int li) -> bool {
-                        if (l_len[li] < min_length) return false;
-                        const int rr = l_minrow[li], cc = l_mincol[li];
-                        double val;
-                        if (rr == 0) val = row0[cc];
-                        else {
-                            const int w = rr + 1, npts = min(10 * w, n);
-                            // recompute the ricker taps of that width on the fly (one lane)
-                            const double a = (double)w, Aa = 2.0 / (sqrt(3.0 * a) * pow(3.14159265358979323846, 0.25));
-                            const int c0 = (npts - 1) / 2;
-                            int t_lo = max(cc + c0 - (npts - 1), 0), t_hi = min(cc + c0, n - 1);
-                            double acc = 0.0;
-                            for (int t = t_lo; t <= t_hi; ++t) {
-                                double vec = (double)(cc + c0 - t) - ((double)npts - 1.0) / 2.0;
-                                double xsq = vec * vec;
-                                double h = Aa * (1.0 - xsq / (a * a)) * exp(-xsq / (2.0 * a * a));
-                                acc = fma((double)xs[t], h, acc);
-                            }
-                            val = acc;
-                        }
-                        const int ws = max(cc - hf, 0), we = min(cc + hf + odd, n);
-                        for (int q = ws; q < we; ++q) tmp[q - ws] = row0[q];
-                        const double noise = percentile10(tmp, we - ws);
-                        const double snr = fabs(val / noise);
-                        return !(snr < 1.0);
-                    };
-                    // start row: the largest row that has any local maximum
-                    int start = -1;
+                    // start row: the largest row that has any local maximum; its maxima seed the ridge lines
                     for (int r = nrows - 1; r >= 0 && start < 0; --r) {
                         const unsigned* bits = maxbits + (size_t)r * Y.nwords;
                         for (int wd = 0; wd < Y.nwords; ++wd) if (bits[wd]) { start = r; break; }
                     }
                     if (start >= 0) {
-                        {
-                            const unsigned* bits = maxbits + (size_t)start * Y.nwords;
-                            for (int c = 0; c < n; ++c)
-                                if ((bits[c >> 5] >> (c & 31)) & 1u) {
-                                    if (nl < LCAP) { l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)start; l_mincol[nl] = (short)c; ++nl; }
-                                }
+                        const unsigned* bits = maxbits + (size_t)start * Y.nwords;
+                        for (int wd = 0; wd * 32 < n; ++wd) {
+                            unsigned word = bits[wd];
+                            while (word) {
+                                int c = wd * 32 + __ffs(word) - 1;
+                                word &= word - 1;
+                                if (nl < LCAP) { l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)start; l_mincol[nl] = (short)c; ++nl; }
+                            }
                         }
-                        for (int r = start - 1; r >= 0; --r) {
-                            const unsigned* bits = maxbits + (size_t)r * Y.nwords;
-                            const int maxd = (r + 1) / 4;                  // floor(widths[r] / 4), diffs are integers
-                            // snapshot: column -> first line (list order) whose last column is that column
-                            for (int c = 0; c < n; ++c) colmap[c] = -1;
-                            for (int li = nl - 1; li >= 0; --li) { l_gap[li] += 1; colmap[l_last[li]] = (short)li; }
-                            const int nl_snapshot = nl;
-                            for (int c = 0; c < n; ++c) {
-                                if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
+                    }
+                }
+                start = __shfl_sync(FULL, start, 0);
+                for (int r = start - 1; r >= 0; --r) {
+                    for (int c = lane; c < n; c += 32) colmap[c] = -1;
+                    __syncwarp();
+                    if (lane == 0) {
+                        const unsigned* bits = maxbits + (size_t)r * Y.nwords;
+                        const int maxd = (r + 1) / 4;                  // floor(widths[r] / 4); distances are integers
+                        // snapshot: column -> first line (list order) whose last column is that column
+                        for (int li = nl - 1; li >= 0; --li) { l_gap[li] += 1; colmap[l_last[li]] = (short)li; }
+                        const int nl_snapshot = nl;
+                        for (int wd = 0; wd * 32 < n; ++wd) {
+                            unsigned word = bits[wd];
+                            while (word) {
+                                const int c = wd * 32 + __ffs(word) - 1;
+                                word &= word - 1;
                                 int best = -1;
                                 if (nl_snapshot > 0) {
                                     // np.argmin(|c - prev|): the smallest distance wins, first in list order on
@@ -308,19 +312,22 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                                     l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)r; l_mincol[nl] = (short)c; ++nl;
                                 }
                             }
-                            // retire lines whose gap exceeds gap_thresh = ceil(widths[0]) = 1 (order preserved)
-                            int keep = 0;
-                            for (int li = 0; li < nl; ++li) {
-                                if (l_gap[li] > 1) { if (accept(li)) ++result; }
-                                else {
-                                    if (keep != li) { l_last[keep] = l_last[li]; l_gap[keep] = l_gap[li]; l_len[keep] = l_len[li]; l_minrow[keep] = l_minrow[li]; l_mincol[keep] = l_mincol[li]; }
-                                    ++keep;
-                                }
-                            }
-                            nl = keep;
                         }
-                        for (int li = 0; li < nl; ++li) if (accept(li)) ++result;
+                        // retire lines whose gap exceeds gap_thresh = ceil(widths[0]) = 1 (order preserved)
+                        int keep = 0;
+                        for (int li = 0; li < nl; ++li) {
+                            if (l_gap[li] > 1) { if (accept(li)) ++result; }
+                            else {
+                                if (keep != li) { l_last[keep] = l_last[li]; l_gap[keep] = l_gap[li]; l_len[keep] = l_len[li]; l_minrow[keep] = l_minrow[li]; l_mincol[keep] = l_mincol[li]; }
+                                ++keep;
+                            }
+                        }
+                        nl = keep;
                     }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    for (int li = 0; li < nl; ++li) if (accept(li)) ++result;
                     orow[d0.col] = (double)result;
                 }
                 __syncwarp();
@@ -349,12 +356,13 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     Y.lz_lanes = need_lz ? LZ_LANES : 0;
     size_t off = 0;
     const bool need_cwt = Y.cwt_n > 0;
-    off += need_cwt ? (size_t)A.npad * 8 : 0;              // row0
-    Y.off_tmp = (int)off;   off += need_cwt ? (size_t)A.npad * 8 : 0;
+    off += need_cwt ? (size_t)Y.cwt_n * A.npad * 8 : 0;    // rows
+    Y.off_noise = (int)off; off += need_cwt ? (size_t)A.npad * 8 : 0;
     Y.off_hw = (int)off;    off += need_cwt ? (size_t)TSFX_MAXW_PTS * 8 : 0;
     Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
     Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * 3 * (A.npad + 1) * 2;
     off = (off + 3) & ~(size_t)3;
+    Y.off_sym = (int)off;   off += (size_t)Y.lz_lanes * A.npad * 2;
     Y.off_bits = (int)off;  off += need_cwt ? (size_t)Y.cwt_n * Y.nwords * 4 : 0;
     Y.off_lines = (int)off; off += need_cwt ? (size_t)5 * 2 * A.npad * 2 : 0;
     Y.off_map = (int)off;   off += need_cwt ? (size_t)A.npad * 2 : 0;

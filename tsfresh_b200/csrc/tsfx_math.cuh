@@ -7,8 +7,10 @@
 
 #ifdef __CUDACC__
 #define TSFX_HD __host__ __device__ __forceinline__
+#define TSFX_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define TSFX_HD inline
+#define TSFX_HD_NOINLINE inline
 #endif
 
 namespace tsfx {
@@ -63,7 +65,7 @@ TSFX_HD double m_incbeta(double a, double b, double x) {
 }
 
 // 2 * stdtr(df, -|t|): the two-sided p-value scipy.stats.linregress reports (_stats_py.py linregress).
-TSFX_HD double m_student_two_sided(double t, double df) {
+TSFX_HD_NOINLINE double m_student_two_sided(double t, double df) {
     if (!(df > 0.0) || t != t) return m_nan();
     double t2 = t * t;
     if (isinf(t2)) return 0.0;
@@ -85,12 +87,12 @@ TSFX_HD double m_mackinnon_p_c(double stat) {
 }
 
 // ------------------------------------------------------------------ linregress finishing step
-struct LinReg { double pvalue, rvalue, intercept, slope, stderr_; };
+struct LinReg { double rvalue, intercept, slope, stderr_, tstat, df; };
 
 // scipy.stats.linregress from the averaged centred sums (ssxm, ssym, ssxym), the means and n.
 TSFX_HD LinReg m_linregress(double n, double xmean, double ymean, double ssxm, double ssym, double ssxym) {
     LinReg R;
-    if (n < 2.0) { R.pvalue = R.rvalue = R.intercept = R.slope = R.stderr_ = m_nan(); return R; }
+    if (n < 2.0) { R.rvalue = R.intercept = R.slope = R.stderr_ = R.tstat = m_nan(); R.df = n - 2.0; return R; }
     double r;
     if (ssxm == 0.0 || ssym == 0.0) r = (ssxym == 0.0) ? m_nan() : 0.0;
     else {
@@ -103,7 +105,8 @@ TSFX_HD LinReg m_linregress(double n, double xmean, double ymean, double ssxm, d
     R.intercept = ymean - R.slope * xmean;
     double df = n - 2.0;
     double t = r * sqrt(df / ((1.0 - r + 1e-20) * (1.0 + r + 1e-20)));
-    R.pvalue = m_student_two_sided(t, df);
+    R.tstat = t;          // the p-value (an incomplete-beta evaluation) is formed only when asked for
+    R.df = df;
     // df == 0 (two points): r is +-1 up to rounding, so scipy's (1 - r^2) * ssym / ssxm / 0 is 0/0 = NaN
     // or tiny/0 = inf depending on the last bit of r; the mathematically exact value is returned here.
     R.stderr_ = (df == 0.0) ? m_nan() : sqrt((1.0 - r * r) * ssym / ssxm / df);
@@ -112,7 +115,7 @@ TSFX_HD LinReg m_linregress(double n, double xmean, double ymean, double ssxm, d
 
 TSFX_HD double m_linreg_pick(const LinReg& R, int attr) {
     switch (attr) {
-        case 0: return R.pvalue;
+        case 0: return m_student_two_sided(R.tstat, R.df);
         case 1: return R.rvalue;
         case 2: return R.intercept;
         case 3: return R.slope;
