@@ -1,0 +1,47 @@
+// k_assemble.cu -- scatters the per-group staging matrices into the final [n_series x ncols] matrix
+// (the dense float64 result PartitionedTsData.pivot would build, tsfresh/feature_extraction/data.py:86-121).
+// One warp per row: coalesced reads of the staging rows into shared memory at their final column,
+// then one coalesced write of the whole row.  Pure HBM traffic: 16 bytes per feature value.
+#include <algorithm>
+
+#include "tsfx_common.cuh"
+#include "tsfx_kernels.h"
+
+namespace tsfx {
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_assemble(AssembleArgs A, int row_pad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* row = reinterpret_cast<double*>(smem_raw) + (size_t)warp * row_pad;
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.n_series; s += warps_total) {
+        for (int j = lane; j < A.ncols; j += 32) row[j] = dnan();      // columns no descriptor covers
+        __syncwarp();
+        for (int g = 0; g < A.n_groups; ++g) {
+            const int c0 = A.cum[g], w = A.cum[g + 1] - c0;
+            if (w == 0) continue;
+            const double* src = A.stage + (size_t)A.n_series * c0 + (size_t)s * w;
+            for (int j = lane; j < w; j += 32) row[__ldg(A.final_col + c0 + j)] = __ldcs(src + j);
+        }
+        __syncwarp();
+        double* dst = A.out + (size_t)s * A.ncols;
+        for (int j = lane; j < A.ncols; j += 32) __stcs(dst + j, row[j]);
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count) {
+    const int row_pad = (A.ncols + 1) & ~1;
+    constexpr int WPC = 8;
+    size_t smem = (size_t)WPC * row_pad * sizeof(double);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k_assemble<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (A.n_series + WPC - 1) / WPC;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)sm_count * 8));
+    k_assemble<WPC><<<grid, WPC * 32, smem, st>>>(A, row_pad);
+    return cudaGetLastError();
+}
+
+}  // namespace tsfx

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
         // caches for multi-column calculators
         int lt_key = -1; LinReg lt_fit;
         bool lin_done = false; LinReg lin_fit;
-        bool pacf_done = false;
+        bool pacf_done = false, peaks_done = false;
 
         for (int j = 0; j < A.nd; ++j) {
             const Desc d = A.descs[j];
@@ -383,16 +383,37 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
                     break;
                 }
                 case TSFX_NUMBER_PEAKS: {
-                    int sup = d.i0, c = 0;
-                    for (int b0 = sup; b0 < n - sup; b0 += 32) {
-                        int i = b0 + lane;
-                        bool p = i < n - sup;
-                        if (p) {
-                            float v = xs[i];
-                            for (int q = 1; q <= sup; ++q)
-                                if (!(v > xs[i - q] && v > xs[i + q])) { p = false; break; }
+                    // support radius of every point (largest q with x[i] > x[i-j], x[i] > x[i+j] for all j <= q),
+                    // formed once for the whole run of number_peaks descriptors; number_peaks(n) = #{radius >= n}
+                    unsigned char* rad = reinterpret_cast<unsigned char*>(scr);
+                    if (!peaks_done) {
+                        int supmax = 1;
+                        for (int jj = j; jj < A.nd && A.descs[jj].calc == TSFX_NUMBER_PEAKS; ++jj) supmax = max(supmax, A.descs[jj].i0);
+                        supmax = min(supmax, 255);
+                        for (int i = lane; i < n; i += 32) {
+                            const float v = xs[i];
+                            const int lim = min(min(i, n - 1 - i), supmax);
+                            int q = 0;
+                            while (q < lim && v > xs[i - q - 1] && v > xs[i + q + 1]) ++q;
+                            rad[i] = (unsigned char)q;
                         }
-                        c += wcount(p);
+                        __syncwarp();
+                        peaks_done = true;
+                    }
+                    int sup = d.i0, c = 0;
+                    if (sup <= 255) {
+                        for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && (int)rad[i] >= sup); }
+                    } else {
+                        for (int b0 = sup; b0 < n - sup; b0 += 32) {
+                            int i = b0 + lane;
+                            bool p = i < n - sup;
+                            if (p) {
+                                float v = xs[i];
+                                for (int q = 1; q <= sup; ++q)
+                                    if (!(v > xs[i - q] && v > xs[i + q])) { p = false; break; }
+                            }
+                            c += wcount(p);
+                        }
                     }
                     r = (double)c;
                     break;

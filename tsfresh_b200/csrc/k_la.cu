@@ -23,41 +23,29 @@ __host__ __device__ inline int adf_maxlag(int n) {
     return m < cap ? m : cap;
 }
 
-// regressor c of row t for the ADF design: 0 const, 1 level (centred), c>=2: d[t-(c-1)]
-__device__ __forceinline__ double adf_reg(int c, int t, const double* lev, const double* dx) {
-    if (c == 0) return 1.0;
-    if (c == 1) return lev[t];
-    return dx[t - (c - 1)];
-}
-
-// Gram of the columns `cols[0..q)` (indices into the ADF regressor set) over rows t0..t1-1, plus X'y and y'y.
-// Layout: G row-major q x q (lower triangle filled), b[q], yy.  One entry per lane and round.
-__device__ __forceinline__ void adf_gram(const int* colmap, int q, int t0, int t1, const double* lev, const double* dx,
-                                         double* G, double* b, double* yy, int lane) {
-    const int ntri = q * (q + 1) / 2;
-    const int total = ntri + q + 1;
-    for (int e = lane; e < total; e += 32) {
-        int a = 0, c = 0, kind;                 // kind 0: G[a][c], 1: b[a], 2: yy
-        if (e < ntri) {
-            // invert e = a(a+1)/2 + c, c <= a
-            a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-            while (a * (a + 1) / 2 > e) --a;
-            while ((a + 1) * (a + 2) / 2 <= e) ++a;
-            c = e - a * (a + 1) / 2;
-            kind = 0;
-        } else if (e < ntri + q) { a = e - ntri; kind = 1; }
-        else kind = 2;
-        const int ca = colmap ? colmap[a] : a, cc = colmap ? colmap[c] : c;
-        double acc = 0.0;
-        for (int t = t0; t < t1; ++t) {
-            double y = dx[t];
-            double va = (kind == 2) ? y : adf_reg(ca, t, lev, dx);
-            double vb = (kind == 0) ? adf_reg(cc, t, lev, dx) : y;
-            acc = fma(va, vb, acc);
+// Lag-product block of one sequence over the row window [t0, T):
+//   P[i*ldp + j] = sum_t seq[t-i] * seq[t-j]   (0 <= j <= i <= M),   C[i] = sum_t seq[t-i],
+//   and, when `lev` is given, Lv[i] = sum_t lev[t] * seq[t-i].
+// Lane d forms the three full sums of lag distance d once; every other entry on that diagonal follows
+// from the sliding-window identity S_d(i+1) = S_d(i) + seq[t0-i-1] seq[t0-i-1-d] - seq[T-1-i] seq[T-1-i-d],
+// so the whole block costs O(M * rows + M^2) instead of O(M^2 * rows).  Requires t0 >= M.
+__device__ __forceinline__ void lag_gram(const double* seq, const double* lev, int t0, int T, int M, double* P, int ldp,
+                                         double* C, double* Lv, int lane) {
+    for (int d = lane; d <= M; d += 32) {
+        double s = 0.0, c = 0.0, l = 0.0;
+        for (int t = t0; t < T; ++t) {
+            const double v = seq[t - d];
+            s = fma(seq[t], v, s);
+            c += v;
+            if (lev) l = fma(lev[t], v, l);
         }
-        if (kind == 0) G[a * q + c] = acc;
-        else if (kind == 1) b[a] = acc;
-        else *yy = acc;
+        C[d] = c;
+        if (lev) Lv[d] = l;
+        P[d * ldp + 0] = s;                          // (i, j) = (d, 0)
+        for (int i = 0; i + 1 + d <= M; ++i) {       // slide the window one step back in time
+            s += seq[t0 - i - 1] * seq[t0 - i - 1 - d] - seq[T - 1 - i] * seq[T - 1 - i - d];
+            P[(i + 1 + d) * ldp + (i + 1)] = s;
+        }
     }
     __syncwarp();
 }
@@ -113,8 +101,10 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
     double* G = dx + A.npad;                               // pmax*pmax
     double* bvec = G + pmax * pmax;                        // pmax
     double* res = bvec + pmax;                             // 8 : staged results
-    int* colmap = reinterpret_cast<int*>(res + 8);         // pmax ints (pmax is even)
-    float* xs = reinterpret_cast<float*>(colmap + ((pmax + 3) & ~3));
+    double* Pm = res + 8;                                  // pmax*pmax : lag-product block
+    double* Cv = Pm + pmax * pmax;                         // pmax
+    double* Lv = Cv + pmax;                                // pmax
+    float* xs = reinterpret_cast<float*>(Lv + pmax);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
     for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
@@ -138,24 +128,13 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                     if (ar_ok) {
                         const int q = k + 1;
                         // columns: 0 const, j>=1: xc[t-j]; target xc[t]; rows t = k..n-1
-                        const int ntri = q * (q + 1) / 2, total = ntri + q;
-                        for (int e = lane; e < total; e += 32) {
-                            int a, c;
-                            bool rhs = e >= ntri;
-                            if (!rhs) {
-                                a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-                                while (a * (a + 1) / 2 > e) --a;
-                                while ((a + 1) * (a + 2) / 2 <= e) ++a;
-                                c = e - a * (a + 1) / 2;
-                            } else { a = e - ntri; c = 0; }
-                            double acc = 0.0;
-                            for (int t = k; t < n; ++t) {
-                                double va = a == 0 ? 1.0 : xc[t - a];
-                                double vb = rhs ? xc[t] : (c == 0 ? 1.0 : xc[t - c]);
-                                acc = fma(va, vb, acc);
-                            }
-                            if (rhs) bvec[a] = acc; else G[a * q + c] = acc;
+                        lag_gram(xc, nullptr, k, n, k, Pm, pmax, Cv, nullptr, lane);
+                        for (int e = lane; e < q * q; e += 32) {
+                            const int a = e / q, c = e - a * q;
+                            if (c > a) continue;
+                            G[a * q + c] = (a == 0) ? (double)rows : (c == 0 ? Cv[a] : Pm[a * pmax + c]);
                         }
+                        for (int a = lane; a < q; a += 32) bvec[a] = (a == 0) ? Cv[0] : Pm[a * pmax + 0];
                         __syncwarp();
                         int good = 0;
                         if (M.vmax == M.vmin) {
@@ -192,7 +171,25 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                         if (adf_mode != TSFX_AUTOLAG_NONE) {
                             const int p = M0 + 2, t0 = M0, nobs = nd_ - M0;
                             double* yy = res + 7;
-                            adf_gram(nullptr, p, t0, nd_, xc, dx, G, bvec, yy, lane);
+                            // columns [const, level, dlag1..dlagM]; y = dx[t] = "dlag0"
+                            lag_gram(dx, xc, t0, nd_, M0, Pm, pmax, Cv, Lv, lane);
+                            {
+                                double l1 = 0.0, l2 = 0.0;
+                                for (int t = t0 + lane; t < nd_; t += 32) { double v = xc[t]; l1 += v; l2 = fma(v, v, l2); }
+                                l1 = wsum(l1); l2 = wsum(l2);
+                                for (int e = lane; e < p * p; e += 32) {
+                                    const int a = e / p, c = e - a * p;
+                                    if (c > a) continue;
+                                    double v;
+                                    if (a == 0) v = (double)nobs;
+                                    else if (a == 1) v = (c == 0) ? l1 : l2;
+                                    else v = (c == 0) ? Cv[a - 1] : (c == 1 ? Lv[a - 1] : Pm[(a - 1) * pmax + (c - 1)]);
+                                    G[a * p + c] = v;
+                                }
+                                for (int a = lane; a < p; a += 32) bvec[a] = (a == 0) ? Cv[0] : (a == 1 ? Lv[0] : Pm[(a - 1) * pmax + 0]);
+                                if (lane == 0) *yy = Pm[0];
+                                __syncwarp();
+                            }
                             int best_q = 2;
                             {
                                 // factorise as far as the pivots stay positive (the models are nested)
@@ -222,10 +219,25 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                         }
                         // final regression on the longer sample, columns [const, dlag1..dlagU, level]
                         const int q = used + 2, t0 = used, nobs = nd_ - used;
-                        for (int c = lane; c < q; c += 32) colmap[c] = (c == 0) ? 0 : (c == q - 1 ? 1 : c + 1);
-                        __syncwarp();
                         double* yy = res + 7;
-                        adf_gram(colmap, q, t0, nd_, xc, dx, G, bvec, yy, lane);
+                        lag_gram(dx, xc, t0, nd_, used, Pm, pmax, Cv, Lv, lane);
+                        {
+                            double l1 = 0.0, l2 = 0.0;
+                            for (int t = t0 + lane; t < nd_; t += 32) { double v = xc[t]; l1 += v; l2 = fma(v, v, l2); }
+                            l1 = wsum(l1); l2 = wsum(l2);
+                            for (int e = lane; e < q * q; e += 32) {
+                                const int a = e / q, c = e - a * q;
+                                if (c > a) continue;
+                                double v;
+                                if (a == 0) v = (double)nobs;
+                                else if (a < q - 1) v = (c == 0) ? Cv[a] : Pm[a * pmax + c];
+                                else v = (c == 0) ? l1 : (c == q - 1 ? l2 : Lv[c]);
+                                G[a * q + c] = v;
+                            }
+                            for (int a = lane; a < q; a += 32) bvec[a] = (a == 0) ? Cv[0] : (a < q - 1 ? Pm[a * pmax + 0] : Lv[0]);
+                            if (lane == 0) *yy = Pm[0];
+                            __syncwarp();
+                        }
                         if (warp_cholesky(G, q, q, lane) == q) {
                             warp_forward(G, q, q, bvec, lane);
                             double ssr = 0.0;
@@ -252,9 +264,9 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
 cudaError_t launch_la(const LaArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     LaArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    int pmax = std::max(adf_maxlag(max_len) + 2, 34);       // 33 covers ar k <= 32
+    int pmax = std::max(adf_maxlag(max_len) + 2, A.nscr + 1);   // nscr carries the plan's largest AR order k
     pmax = (pmax + 1) & ~1;
-    size_t per = (size_t)A.npad * 16 + (size_t)pmax * pmax * 8 + (size_t)pmax * 8 + 64 + (size_t)((pmax + 3) & ~3) * 4 + (size_t)A.npad * 4;
+    size_t per = (size_t)A.npad * 16 + (size_t)pmax * pmax * 16 + (size_t)pmax * 24 + 64 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     if (per > 227 * 1024) return cudaErrorInvalidConfiguration;

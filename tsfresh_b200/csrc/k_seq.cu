@@ -18,7 +18,7 @@ namespace tsfx {
 #define LZ_LANES 8
 
 struct SeqLayout {
-    int npad, npow2, nwords, lz_lanes, cwt_n;
+    int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride;
     int off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs;   // byte offsets
 };
 
@@ -85,20 +85,27 @@ __device__ __forceinline__ void ricker_fill(double* hw, int npts, int w, int lan
     __syncwarp();
 }
 
-// scipy.stats.scoreatpercentile(win[0..wlen), 10) by rank selection (no scratch, read-only window)
+// scipy.stats.scoreatpercentile(win[0..wlen), 10): the order statistics i = floor(0.1 (wlen-1)) and i+1 are
+// found by successive minima over (value, index) pairs -- no scratch, read-only window, O(wlen * (i+2)).
 __device__ __forceinline__ double percentile10(const double* win, int wlen) {
-    double idx = 10.0 / 100.0 * (double)(wlen - 1);
-    int i = (int)idx;
-    double v0 = 0.0, v1 = 0.0;
-    for (int a = 0; a < wlen; ++a) {
-        double va = win[a];
-        int rk = 0;
-        for (int b = 0; b < wlen; ++b) { double vb = win[b]; rk += (vb < va) || (vb == va && b < a); }
-        if (rk == i) v0 = va;
-        if (rk == i + 1) v1 = va;
+    const double idx = 10.0 / 100.0 * (double)(wlen - 1);
+    const int i = (int)idx;
+    double pv = 0.0, v0 = 0.0, v1 = 0.0;
+    int pi = -1;
+    for (int r = 0; r <= i + 1 && r < wlen; ++r) {
+        double bv = 0.0;
+        int bi = -1;
+        for (int a = 0; a < wlen; ++a) {
+            const double va = win[a];
+            const bool after = (pi < 0) || (va > pv) || (va == pv && a > pi);
+            if (after && (bi < 0 || va < bv)) { bv = va; bi = a; }
+        }
+        pv = bv; pi = bi;
+        if (r == i) v0 = bv;
+        if (r == i + 1) v1 = bv;
     }
     if ((double)i == idx) return v0;
-    double w0 = (double)(i + 1) - idx, w1 = idx - (double)i;
+    const double w0 = (double)(i + 1) - idx, w1 = idx - (double)i;
     return (v0 * w0 + v1 * w1) / (w0 + w1);
 }
 
@@ -142,25 +149,29 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                     for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
                 }
                 __syncwarp();
+                // phrase dictionary = prefix-closed trie, stored as an open-addressing hash of (parent, symbol) -> node
+                for (int q = lane; q < cnt * Y.lz_hash; q += 32) trie[(size_t)(q / Y.lz_hash) * Y.lz_stride + (q % Y.lz_hash)] = 0;
+                __syncwarp();
                 if (lane < cnt) {
                     const Desc d = A.descs[j + lane];
                     const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
-                    unsigned short* first = trie + (size_t)lane * 3 * (Y.npad + 1);
-                    unsigned short* next = first + (Y.npad + 1);
-                    unsigned short* sym = next + (Y.npad + 1);
+                    unsigned short* htab = trie + (size_t)lane * Y.lz_stride;         // lz_hash slots, 0 = empty
+                    unsigned short* par = htab + Y.lz_hash;                            // npad + 1
+                    unsigned short* sym = par + (Y.npad + 1);                          // npad + 1
+                    const unsigned mask = (unsigned)Y.lz_hash - 1u;
                     int nodes = 1, node = 0, phrases = 0;
-                    first[0] = 0;                                   // 0 = no child (root is node 0)
                     for (int pos = 0; pos < n; ++pos) {
-                        int sy = sb[pos];
-                        int ch = first[node];
-                        while (ch != 0 && sym[ch] != sy) ch = next[ch];
-                        if (ch != 0) node = ch;
+                        const unsigned sy = sb[pos];
+                        unsigned h = ((unsigned)node * 0x9E3779B1u + sy * 0x85EBCA77u) >> 12;
+                        h &= mask;
+                        unsigned ch;
+                        while ((ch = htab[h]) != 0u && !(par[ch] == node && sym[ch] == sy)) h = (h + 1u) & mask;
+                        if (ch != 0u) node = (int)ch;
                         else {
-                            int nn = nodes++;
+                            const int nn = nodes++;
+                            par[nn] = (unsigned short)node;
                             sym[nn] = (unsigned short)sy;
-                            first[nn] = 0;
-                            next[nn] = first[node];
-                            first[node] = (unsigned short)nn;
+                            htab[h] = (unsigned short)nn;
                             ++phrases;
                             node = 0;
                         }
@@ -353,14 +364,17 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     // which pieces does this plan need?  (nscr carries flags from the API: bit0 lz, bit1 perm, bits 8.. cwt_n)
     const bool need_lz = (A.nscr & 1) != 0, need_perm = (A.nscr & 2) != 0;
     Y.cwt_n = (A.nscr >> 8) & 0xff;
-    Y.lz_lanes = need_lz ? LZ_LANES : 0;
+    Y.lz_lanes = need_lz ? std::min(LZ_LANES, std::max(1, (A.nscr >> 16) & 0xff)) : 0;
+    Y.lz_hash = 4;
+    while (Y.lz_hash < 2 * (A.npad + 1)) Y.lz_hash <<= 1;
+    Y.lz_stride = Y.lz_hash + 2 * (A.npad + 1);
     size_t off = 0;
     const bool need_cwt = Y.cwt_n > 0;
     off += need_cwt ? (size_t)Y.cwt_n * A.npad * 8 : 0;    // rows
     Y.off_noise = (int)off; off += need_cwt ? (size_t)A.npad * 8 : 0;
     Y.off_hw = (int)off;    off += need_cwt ? (size_t)TSFX_MAXW_PTS * 8 : 0;
     Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
-    Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * 3 * (A.npad + 1) * 2;
+    Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * Y.lz_stride * 2;
     off = (off + 3) & ~(size_t)3;
     Y.off_sym = (int)off;   off += (size_t)Y.lz_lanes * A.npad * 2;
     Y.off_bits = (int)off;  off += need_cwt ? (size_t)Y.cwt_n * Y.nwords * 4 : 0;

@@ -30,7 +30,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-static const char* kGroupNames[G_COUNT] = {"basic", "sorted", "spectral", "la", "entropy", "seq"};
+static const char* kGroupNames[G_EVENTS] = {"basic", "sorted", "spectral", "la", "entropy", "seq", "assemble"};
 
 struct tsfx_ctx {
     int device = 0;
@@ -38,13 +38,13 @@ struct tsfx_ctx {
     bool own_stream = false;
     int sm_count = 148;
     std::string err;
-    DevBuf values, begin, len, out, misc;
+    DevBuf values, begin, len, out, misc, stage;
     double* d_dec = nullptr;
     double2* d_tw = nullptr;
     int tw_n = 0;
-    cudaEvent_t ev[G_COUNT][2];
-    bool ev_used[G_COUNT];
-    float ms[G_COUNT];
+    cudaEvent_t ev[G_EVENTS][2];
+    bool ev_used[G_EVENTS];
+    float ms[G_EVENTS];
     int launches = 0;
     CsrWorkspace csr;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
@@ -54,12 +54,14 @@ struct tsfx_plan {
     tsfx_ctx* ctx = nullptr;
     std::vector<Desc> host[G_COUNT];
     Desc* dev[G_COUNT] = {nullptr};
+    int32_t* d_final_col = nullptr;   // final column of every staged column, groups concatenated
+    int cum[G_COUNT + 1] = {0};
     int ncols = 0;
     int lag_needed = 0, pacf_want = -1;
     int basic_bins = 0, fourier_bins = 0;
     int need_fft = 0, need_welch = 0;
     int max_ar_k = 0, need_adf = 0;
-    int max_lz_bins = 0, max_perm_dim = 0, max_cwt_peaks_n = 0;
+    int max_lz_bins = 0, max_perm_dim = 0, max_cwt_peaks_n = 0, n_lz = 0;
     int friedrich_r = 0;
     double* d_tables = nullptr;
     int64_t* d_toff = nullptr;
@@ -120,7 +122,7 @@ extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
     ctx = new (std::nothrow) tsfx_ctx();
     if (!ctx) return fail(nullptr, TSFX_E_NOMEM, "out of host memory");
     ctx->device = device;
-    for (int g = 0; g < G_COUNT; ++g) { ctx->ev_used[g] = false; ctx->ms[g] = 0.f; ctx->ev[g][0] = ctx->ev[g][1] = nullptr; }
+    for (int g = 0; g < G_EVENTS; ++g) { ctx->ev_used[g] = false; ctx->ms[g] = 0.f; ctx->ev[g][0] = ctx->ev[g][1] = nullptr; }
 #define CKC(call)                                                                                     \
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
@@ -136,7 +138,7 @@ extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
     else { CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-    for (int g = 0; g < G_COUNT; ++g) { CKC(cudaEventCreate(&ctx->ev[g][0])); CKC(cudaEventCreate(&ctx->ev[g][1])); }
+    for (int g = 0; g < G_EVENTS; ++g) { CKC(cudaEventCreate(&ctx->ev[g][0])); CKC(cudaEventCreate(&ctx->ev[g][1])); }
     // decimal threshold table d * 10^k (correctly rounded literals via strtod)
     {
         std::vector<double> dec((TSFX_DEC_MAX - TSFX_DEC_MIN + 1) * 9);
@@ -158,11 +160,11 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release();
+    ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release(); ctx->stage.release();
     ctx->csr.release();
     if (ctx->d_dec) cudaFree(ctx->d_dec);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
-    for (int g = 0; g < G_COUNT; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
+    for (int g = 0; g < G_EVENTS; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -216,7 +218,7 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
             case TSFX_APPROXIMATE_ENTROPY:
                 if (d.i0 != 2) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "approximate_entropy: only m=2"); }
                 break;
-            case TSFX_LEMPEL_ZIV_COMPLEXITY: P->max_lz_bins = std::max(P->max_lz_bins, d.i0); break;
+            case TSFX_LEMPEL_ZIV_COMPLEXITY: P->max_lz_bins = std::max(P->max_lz_bins, d.i0); P->n_lz += 1; break;
             case TSFX_PERMUTATION_ENTROPY:
                 if (d.i1 < 2 || d.i1 > 8 || d.i0 < 1) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "permutation_entropy: dimension 2..8, tau >= 1"); }
                 P->max_perm_dim = std::max(P->max_perm_dim, d.i1);
@@ -233,6 +235,7 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
         }
     }
     if (P->lag_needed > 4096) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "lag > 4096"); }
+    std::vector<int32_t> final_col;
     for (int g = 0; g < G_COUNT; ++g) {
         std::stable_sort(P->host[g].begin(), P->host[g].end(), [](const Desc& a, const Desc& b) {
             if (a.calc != b.calc) return a.calc < b.calc;
@@ -243,12 +246,22 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
             if (a.i0 != b.i0) return a.i0 < b.i0;
             return a.col < b.col;
         });
+        P->cum[g + 1] = P->cum[g] + (int)P->host[g].size();
+        for (size_t j = 0; j < P->host[g].size(); ++j) {      // col becomes the index inside the group's staging row
+            final_col.push_back(P->host[g][j].col);
+            P->host[g][j].col = (int32_t)j;
+        }
         if (!P->host[g].empty()) {
             size_t bytes = P->host[g].size() * sizeof(Desc);
             cudaError_t e = cudaMalloc(&P->dev[g], bytes);
             if (e == cudaSuccess) e = cudaMemcpy(P->dev[g], P->host[g].data(), bytes, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_CUDA, cudaGetErrorString(e)); }
         }
+    }
+    if (!final_col.empty()) {
+        cudaError_t e = cudaMalloc(&P->d_final_col, final_col.size() * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_final_col, final_col.data(), final_col.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_CUDA, cudaGetErrorString(e)); }
     }
     if (n_tables > 0) {
         if (!tables || !table_off || !table_half) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_INVALID, "cwt tables missing"); }
@@ -272,6 +285,7 @@ extern "C" void tsfx_plan_destroy(tsfx_plan* P) {
     if (!P) return;
     if (P->ctx) cudaSetDevice(P->ctx->device);
     for (int g = 0; g < G_COUNT; ++g) if (P->dev[g]) cudaFree(P->dev[g]);
+    if (P->d_final_col) cudaFree(P->d_final_col);
     if (P->d_tables) cudaFree(P->d_tables);
     if (P->d_toff) cudaFree(P->d_toff);
     if (P->d_thalf) cudaFree(P->d_thalf);
@@ -292,9 +306,14 @@ static int ensure_twiddle(tsfx_ctx* ctx, int n_pow2) {
 
 static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int max_len, double* d_out, uint32_t flags) {
     const bool timing = (flags & TSFX_FLAG_TIMING) != 0;
-    for (int g = 0; g < G_COUNT; ++g) ctx->ev_used[g] = false;
+    for (int g = 0; g < G_EVENTS; ++g) ctx->ev_used[g] = false;
     ctx->launches = 0;
     if (R.n_series == 0) return TSFX_OK;
+    const int staged = P->cum[G_COUNT];
+    if (staged == 0) return TSFX_OK;
+    CK(ctx->stage.reserve((size_t)R.n_series * staged * sizeof(double)));
+    double* const d_final = d_out;
+    (void)d_final;
     if (max_len < 1) return fail(ctx, TSFX_E_INVALID, "series of length < 1");
     auto too_long = [&](const char* g) {
         return fail(ctx, TSFX_E_TOO_LONG, std::string("series length ") + std::to_string(max_len) +
@@ -304,10 +323,12 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         if (P->host[g].empty()) continue;
         if (timing) { CK(cudaEventRecord(ctx->ev[g][0], ctx->stream)); }
         cudaError_t e = cudaSuccess;
+        double* d_out = (double*)ctx->stage.p + (size_t)R.n_series * P->cum[g];      // this group's staging matrix
+        const int g_ncols = (int)P->host[g].size();
         switch (g) {
             case G_BASIC: {
                 BasicArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.lag_needed = P->lag_needed;
                 int pac = P->pacf_want >= 0 ? 4 * (P->pacf_want + 1) : 0;
                 A.pacf_off = P->lag_needed + 1;
@@ -319,14 +340,14 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_SORTED: {
                 SortedArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = even(4 * (P->friedrich_r + 2) + 16);
                 e = launch_sorted(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }
             case G_SPECTRAL: {
                 SpectralArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 int p2 = 1;
                 while (p2 < max_len) p2 <<= 1;
                 if (p2 > max_len) p2 >>= 1;            // largest power of two <= max_len
@@ -342,20 +363,22 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_LA: {
                 LaArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.nscr = P->max_ar_k;
                 e = launch_la(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }
             case G_ENTROPY: {
                 EntropyArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 e = launch_entropy(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }
             case G_SEQ: {
                 SeqArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = P->ncols;
-                A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8);
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
+                         (std::min(P->n_lz, 255) << 16);
                 e = launch_seq(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }
@@ -364,6 +387,18 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("launch ") + kGroupNames[g] + ": " + cudaGetErrorString(e));
         ctx->launches += 1;
         if (timing) { CK(cudaEventRecord(ctx->ev[g][1], ctx->stream)); ctx->ev_used[g] = true; }
+    }
+    {   // scatter the staging matrices into the caller's [n_series x ncols] matrix
+        if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][0], ctx->stream)); }
+        AssembleArgs A;
+        A.stage = (const double*)ctx->stage.p; A.out = d_final; A.n_series = R.n_series; A.ncols = P->ncols;
+        A.n_groups = G_COUNT;
+        for (int g = 0; g <= G_COUNT; ++g) A.cum[g] = P->cum[g];
+        A.final_col = P->d_final_col;
+        cudaError_t e = launch_assemble(A, ctx->stream, ctx->sm_count);
+        if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("launch assemble: ") + cudaGetErrorString(e));
+        ctx->launches += 1;
+        if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][1], ctx->stream)); ctx->ev_used[G_COUNT] = true; }
     }
     return TSFX_OK;
 }
@@ -447,7 +482,7 @@ extern "C" int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     int k = 0;
-    for (int g = 0; g < G_COUNT && k < cap; ++g) {
+    for (int g = 0; g < G_EVENTS && k < cap; ++g) {
         if (!ctx->ev_used[g]) continue;
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[g][0], ctx->ev[g][1]));

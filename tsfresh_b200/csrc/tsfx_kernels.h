@@ -9,6 +9,21 @@
 namespace tsfx {
 
 enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_COUNT };
+#define G_EVENTS (G_COUNT + 1)      // + the assemble pass
+
+// Result assembly: every kernel group writes its own dense [n_series x ncols_g] staging matrix (so each
+// 32-byte sector is completed by the warp that owns the row, while it is still in L2); this pass
+// scatters the staging rows into the final row-major [n_series x ncols] matrix in column order.
+struct AssembleArgs {
+    const double* stage;          // group g starts at stage + n_series * cum[g]
+    double* out;
+    int64_t n_series;
+    int ncols;                    // final row stride
+    int n_groups;
+    int cum[G_COUNT + 1];         // columns before group g (cum[n_groups] = total staged columns)
+    const int32_t* final_col;     // device: final column of staged column (cum[g] + j)
+};
+cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count);
 
 struct BasicArgs {
     SeriesRef R;
