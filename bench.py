@@ -345,7 +345,7 @@ def group_columns(plan):
          "spectral": ["FFT_COEFFICIENT", "FFT_AGGREGATED", "SPKT_WELCH_DENSITY", "FOURIER_ENTROPY", "CWT_COEFFICIENTS"],
          "la": ["AR_COEFFICIENT", "AUGMENTED_DICKEY_FULLER"],
          "entropy": ["SAMPLE_ENTROPY", "APPROXIMATE_ENTROPY"],
-         "seq": ["LEMPEL_ZIV_COMPLEXITY", "PERMUTATION_ENTROPY", "NUMBER_CWT_PEAKS"]}
+         "seq": ["LEMPEL_ZIV_COMPLEXITY", "PERMUTATION_ENTROPY"], "peaks": ["NUMBER_CWT_PEAKS"]}
     rev = {}
     for g, names in G.items():
         for n in names:

@@ -249,7 +249,13 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
     float* xs = reinterpret_cast<float*>(lagS + A.nlag);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
-    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+    // The kernel body is ~250 KB of SASS; warps drifting through different calculators thrash the
+    // instruction cache (ncu: stall_no_instruction dominated).  All warps of a CTA therefore walk the
+    // descriptor list in lock step (one __syncthreads per descriptor): a CTA touches one calculator's code
+    // at a time.  Rows past the end keep participating in the barriers with a duplicate of the last series.
+    for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
+        const bool live = (s0 + warp) < A.R.n_series;
+        const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
         const int n = load_series(A.R, s, xs, lane);
         const Moments M = moments(xs, n, xc, lane);
         const Extra E = extra_pass(xs, xc, n, M, lane);
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
         bool pacf_done = false, peaks_done = false;
 
         for (int j = 0; j < A.nd; ++j) {
+            if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
@@ -601,7 +608,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
                 case TSFX_CONST_NAN:
                 default: r = dnan(); break;
             }
-            if (lane == 0) orow[d.col] = r;
+            if (lane == 0 && live) orow[d.col] = r;
         }
         __syncwarp();
     }

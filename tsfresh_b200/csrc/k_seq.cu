@@ -114,18 +114,11 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
-    double* rows = reinterpret_cast<double*>(base);                       // cwt_n x npad
-    double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad
-    double* hw = reinterpret_cast<double*>(base + Y.off_hw);
-    unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
-    unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
-    short* lines = reinterpret_cast<short*>(base + Y.off_lines);
-    short* colmap = reinterpret_cast<short*>(base + Y.off_map);
+    unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
-    const int LCAP = 2 * Y.npad;
 
     for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
         const int n = load_series(A.R, s, xs, lane);
@@ -133,7 +126,6 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
         float lo = INFINITY, hi = -INFINITY;
         for (int i = lane; i < n; i += 32) { lo = fminf(lo, xs[i]); hi = fmaxf(hi, xs[i]); }
         const double vmin = (double)wminf(lo), vmax = (double)wmaxf(hi);
-        bool cwt_ready = false;
 
         int j = 0;
         while (j < A.nd) {
@@ -185,34 +177,46 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                 double r = dnan();
                 if (n >= D) {
                     const int W = (n - D) / tau + 1;
-                    int m = 2;
-                    while (m < W) m <<= 1;
-                    for (int k = lane; k < m; k += 32) {
-                        unsigned code = 0xffffffffu;
-                        if (k < W) {
-                            const float* w = xs + (size_t)k * tau;
-                            code = 0;
-                            unsigned mul = 1;
-                            for (int p = 0; p < D; ++p) {
-                                float wp = w[p];
-                                unsigned rk = 0;
-                                for (int q = 0; q < D; ++q) { float wq = w[q]; rk += (wq < wp) || (wq == wp && q < p); }
-                                code += rk * mul;
-                                mul *= (unsigned)D;
-                            }
+                    int fact = 1;
+                    for (int q = 2; q <= D; ++q) fact *= q;
+                    // window -> Lehmer index of its rank pattern (ties broken by position: stable order)
+                    auto pattern = [&](int k) -> unsigned {
+                        const float* w = xs + (size_t)k * tau;
+                        unsigned code = 0;
+                        for (int p = 0; p < D; ++p) {
+                            const float wp = w[p];
+                            unsigned c = 0;
+                            for (int q = p + 1; q < D; ++q) c += (w[q] < wp);
+                            code = code * (unsigned)(D - p) + c;
                         }
-                        codes[k] = code;
-                    }
-                    __syncwarp();
-                    warp_bitonic_sort_u32(codes, m, lane);
+                        return code;
+                    };
                     double acc = 0.0;
-                    for (int k = lane; k < W; k += 32) {
-                        unsigned c = codes[k];
-                        if (k == 0 || codes[k - 1] != c) {
-                            int len = 1;
-                            while (k + len < W && codes[k + len] == c) ++len;
-                            double p = (double)len / (double)W;
-                            acc += p * log(p);
+                    if (fact <= Y.npow2) {
+                        // few patterns: shared-memory histogram over the D! indices
+                        for (int b = lane; b < fact; b += 32) codes[b] = 0u;
+                        __syncwarp();
+                        for (int k = lane; k < W; k += 32) atomicAdd(&codes[pattern(k)], 1u);
+                        __syncwarp();
+                        for (int b = lane; b < fact; b += 32) {
+                            const unsigned c = codes[b];
+                            if (c) { double p = (double)c / (double)W; acc += p * log(p); }
+                        }
+                    } else {
+                        // many patterns: sort the indices and count run lengths
+                        int m = 2;
+                        while (m < W) m <<= 1;
+                        for (int k = lane; k < m; k += 32) codes[k] = (k < W) ? pattern(k) : 0xffffffffu;
+                        __syncwarp();
+                        warp_bitonic_sort_u32(codes, m, lane);
+                        for (int k = lane; k < W; k += 32) {
+                            const unsigned c = codes[k];
+                            if (k == 0 || codes[k - 1] != c) {
+                                int len = 1;
+                                while (k + len < W && codes[k + len] == c) ++len;
+                                double p = (double)len / (double)W;
+                                acc += p * log(p);
+                            }
                         }
                     }
                     r = -wsum(acc);
@@ -220,7 +224,39 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                 }
                 if (lane == 0) orow[d0.col] = r;
                 ++j;
-            } else if (d0.calc == TSFX_NUMBER_CWT_PEAKS) {
+            } else {
+                if (lane == 0) orow[d0.col] = dnan();
+                ++j;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    double* rows = reinterpret_cast<double*>(base);                       // cwt_n x npad
+    double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad
+    double* hw = reinterpret_cast<double*>(base + Y.off_hw);
+    unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
+    short* lines = reinterpret_cast<short*>(base + Y.off_lines);
+    short* colmap = reinterpret_cast<short*>(base + Y.off_map);
+    float* xs = reinterpret_cast<float*>(base + Y.off_xs);
+    const int64_t warps_total = (int64_t)gridDim.x * WPC;
+    const int LCAP = 2 * Y.npad;
+
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+        const int n = load_series(A.R, s, xs, lane);
+        double* orow = A.out + (size_t)s * A.ncols;
+        bool cwt_ready = false;
+
+        int j = 0;
+        while (j < A.nd) {
+            const Desc d0 = A.descs[j];
+            if (d0.calc == TSFX_NUMBER_CWT_PEAKS) {
                 if (!cwt_ready) {
                     // all rows 1..cwt_n once (kept in shared memory) + local-maximum bit masks per row
                     for (int w = 1; w <= Y.cwt_n; ++w) {
@@ -352,57 +388,89 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     }
 }
 
+static void seq_geometry(size_t per, int sm_count, int64_t n_series, int* wpc_out, size_t* smem_out, int* grid_out) {
+    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 72 * 1024 / per));
+    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
+    *wpc_out = wpc;
+    *smem_out = per * wpc;
+    int64_t cap = (int64_t)sm_count * 16;
+    *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_series + wpc - 1) / wpc, cap));
+}
+
+#define TSFX_LAUNCH_K(KERNEL, W)                                                                        \
+    {                                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(KERNEL<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                 \
+        KERNEL<W><<<grid, W * 32, smem, st>>>(A, Y);                                                    \
+    }
+
+// lempel_ziv_complexity + permutation_entropy
 cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     SeqArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    SeqLayout Y;
+    if (max_len > 32000) return cudaErrorInvalidConfiguration;
+    SeqLayout Y = {};
     Y.npad = A.npad;
     int p2 = 2;
     while (p2 < max_len) p2 <<= 1;
-    Y.npow2 = p2;
-    Y.nwords = (A.npad + 31) / 32 + 1;
-    // which pieces does this plan need?  (nscr carries flags from the API: bit0 lz, bit1 perm, bits 8.. cwt_n)
+    Y.npow2 = std::max(p2, 1024);                 // >= 6! = 720 so dimensions up to 6 use the histogram path
     const bool need_lz = (A.nscr & 1) != 0, need_perm = (A.nscr & 2) != 0;
-    Y.cwt_n = (A.nscr >> 8) & 0xff;
     Y.lz_lanes = need_lz ? std::min(LZ_LANES, std::max(1, (A.nscr >> 16) & 0xff)) : 0;
     Y.lz_hash = 4;
-    while (Y.lz_hash < 2 * (A.npad + 1)) Y.lz_hash <<= 1;
+    while (Y.lz_hash < A.npad + 2) Y.lz_hash <<= 1;
     Y.lz_stride = Y.lz_hash + 2 * (A.npad + 1);
     size_t off = 0;
-    const bool need_cwt = Y.cwt_n > 0;
-    off += need_cwt ? (size_t)Y.cwt_n * A.npad * 8 : 0;    // rows
-    Y.off_noise = (int)off; off += need_cwt ? (size_t)A.npad * 8 : 0;
-    Y.off_hw = (int)off;    off += need_cwt ? (size_t)TSFX_MAXW_PTS * 8 : 0;
     Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
     Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * Y.lz_stride * 2;
     off = (off + 3) & ~(size_t)3;
     Y.off_sym = (int)off;   off += (size_t)Y.lz_lanes * A.npad * 2;
-    Y.off_bits = (int)off;  off += need_cwt ? (size_t)Y.cwt_n * Y.nwords * 4 : 0;
-    Y.off_lines = (int)off; off += need_cwt ? (size_t)5 * 2 * A.npad * 2 : 0;
-    Y.off_map = (int)off;   off += need_cwt ? (size_t)A.npad * 2 : 0;
     off = (off + 15) & ~(size_t)15;
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
     size_t per = (off + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
-    if (per > 227 * 1024 || max_len > 32000) return cudaErrorInvalidConfiguration;
-    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 100 * 1024 / per));
-    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
-    size_t smem = per * wpc;
-    int64_t cap = (int64_t)sm_count * 16;
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
-#define TSFX_LAUNCH(W)                                                                                  \
-    {                                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(k_seq<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                 \
-        k_seq<W><<<grid, W * 32, smem, st>>>(A, Y);                                                     \
-    }
+    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
+    int wpc, grid;
+    size_t smem;
+    seq_geometry(per, sm_count, A.R.n_series, &wpc, &smem, &grid);
     switch (wpc) {
-        case 8: TSFX_LAUNCH(8) break;
-        case 4: TSFX_LAUNCH(4) break;
-        case 2: TSFX_LAUNCH(2) break;
-        default: TSFX_LAUNCH(1) break;
+        case 8: TSFX_LAUNCH_K(k_seq, 8) break;
+        case 4: TSFX_LAUNCH_K(k_seq, 4) break;
+        case 2: TSFX_LAUNCH_K(k_seq, 2) break;
+        default: TSFX_LAUNCH_K(k_seq, 1) break;
     }
-#undef TSFX_LAUNCH
+    return cudaGetLastError();
+}
+
+// number_cwt_peaks
+cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
+    SeqArgs A = A0;
+    A.npad = (max_len + 3) & ~3;
+    if (max_len > 32000) return cudaErrorInvalidConfiguration;
+    SeqLayout Y = {};
+    Y.npad = A.npad;
+    Y.nwords = (A.npad + 31) / 32 + 1;
+    Y.cwt_n = (A.nscr >> 8) & 0xff;
+    size_t off = 0;
+    off += (size_t)Y.cwt_n * A.npad * 8;                    // rows
+    Y.off_noise = (int)off; off += (size_t)A.npad * 8;
+    Y.off_hw = (int)off;    off += (size_t)TSFX_MAXW_PTS * 8;
+    Y.off_bits = (int)off;  off += (size_t)Y.cwt_n * Y.nwords * 4;
+    Y.off_lines = (int)off; off += (size_t)5 * 2 * A.npad * 2;
+    Y.off_map = (int)off;   off += (size_t)A.npad * 2;
+    off = (off + 15) & ~(size_t)15;
+    Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
+    size_t per = (off + 15) & ~(size_t)15;
+    A.bytes_per_warp = (int)per;
+    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
+    int wpc, grid;
+    size_t smem;
+    seq_geometry(per, sm_count, A.R.n_series, &wpc, &smem, &grid);
+    switch (wpc) {
+        case 8: TSFX_LAUNCH_K(k_peaks, 8) break;
+        case 4: TSFX_LAUNCH_K(k_peaks, 4) break;
+        case 2: TSFX_LAUNCH_K(k_peaks, 2) break;
+        default: TSFX_LAUNCH_K(k_peaks, 1) break;
+    }
     return cudaGetLastError();
 }
 

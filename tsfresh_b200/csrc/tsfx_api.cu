@@ -30,7 +30,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-static const char* kGroupNames[G_EVENTS] = {"basic", "sorted", "spectral", "la", "entropy", "seq", "assemble"};
+static const char* kGroupNames[G_EVENTS] = {"basic", "sorted", "spectral", "la", "entropy", "seq", "peaks", "assemble"};
 
 struct tsfx_ctx {
     int device = 0;
@@ -99,8 +99,10 @@ static int group_of(int calc) {
             return G_LA;
         case TSFX_SAMPLE_ENTROPY: case TSFX_APPROXIMATE_ENTROPY:
             return G_ENTROPY;
-        case TSFX_LEMPEL_ZIV_COMPLEXITY: case TSFX_PERMUTATION_ENTROPY: case TSFX_NUMBER_CWT_PEAKS:
+        case TSFX_LEMPEL_ZIV_COMPLEXITY: case TSFX_PERMUTATION_ENTROPY:
             return G_SEQ;
+        case TSFX_NUMBER_CWT_PEAKS:
+            return G_PEAKS;
         default:
             return G_BASIC;
     }
@@ -380,6 +382,13 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
                          (std::min(P->n_lz, 255) << 16);
                 e = launch_seq(A, max_len, ctx->stream, ctx->sm_count);
+                break;
+            }
+            case G_PEAKS: {
+                SeqArgs A;
+                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.nscr = (P->max_cwt_peaks_n << 8);
+                e = launch_peaks(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }
         }

@@ -8,7 +8,7 @@
 
 namespace tsfx {
 
-enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_COUNT };
+enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_PEAKS, G_COUNT };
 #define G_EVENTS (G_COUNT + 1)      // + the assemble pass
 
 // Result assembly: every kernel group writes its own dense [n_series x ncols_g] staging matrix (so each
@@ -94,6 +94,7 @@ struct SeqArgs {
     int npad, nscr, bytes_per_warp;
 };
 cudaError_t launch_seq(const SeqArgs& A, int max_len, cudaStream_t st, int sm_count);
+cudaError_t launch_peaks(const SeqArgs& A, int max_len, cudaStream_t st, int sm_count);
 
 // plain fill of a column set with NaN is done by BASIC (TSFX_CONST_NAN)
 
