@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
     float* srt = xs + A.npad;
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
-    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+    // lock-step walk of the descriptor list per CTA (see k_basic.cu): keeps the instruction working set small
+    for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
+        const bool live = (s0 + warp) < A.R.n_series;
+        const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
         const int n = load_series(A.R, s, xs, lane);
         int m = 1;
         while (m < n) m <<= 1;
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
         double* coef = scr + (A.nscr - 8);
 
         for (int j = 0; j < A.nd; ++j) {
+            if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
                 }
                 default: break;
             }
-            if (lane == 0) orow[d.col] = r;
+            if (lane == 0 && live) orow[d.col] = r;
         }
         __syncwarp();
     }

@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
     float* xs = reinterpret_cast<float*>(hist + nhist);           // npad
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
-    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
+    // lock-step walk of the descriptor list per CTA (see k_basic.cu): keeps the instruction working set small
+    for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
+        const bool live = (s0 + warp) < A.R.n_series;
+        const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
         const int n = load_series(A.R, s, xs, lane);
         double* orow = A.out + (size_t)s * A.ncols;
 
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
         }
 
         for (int j = 0; j < A.nd; ++j) {
+            if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
                 }
                 default: break;
             }
-            if (lane == 0) orow[d.col] = r;
+            if (lane == 0 && live) orow[d.col] = r;
         }
         __syncwarp();
     }

@@ -48,6 +48,8 @@ struct tsfx_ctx {
     int launches = 0;
     CsrWorkspace csr;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host path
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
 struct tsfx_plan {
@@ -141,6 +143,9 @@ extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
     else { CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     for (int g = 0; g < G_EVENTS; ++g) { CKC(cudaEventCreate(&ctx->ev[g][0])); CKC(cudaEventCreate(&ctx->ev[g][1])); }
+    CKC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) { CKC(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
     // decimal threshold table d * 10^k (correctly rounded literals via strtod)
     {
         std::vector<double> dec((TSFX_DEC_MAX - TSFX_DEC_MIN + 1) * 9);
@@ -167,6 +172,9 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     if (ctx->d_dec) cudaFree(ctx->d_dec);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     for (int g = 0; g < G_EVENTS; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -472,16 +480,34 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
         R.values = values;
         return run_groups(ctx, plan, R, len, out, flags);
     }
-    // host path: pipelined over row blocks so H2D, kernels and D2H of neighbouring blocks overlap
-    size_t ncols = (size_t)plan->ncols;
-    size_t vb = (size_t)n_series * len * sizeof(float), ob = (size_t)n_series * ncols * sizeof(double);
+    // host path: pipelined over row blocks -- the H2D copy of block b+1 and the D2H copy of block b-1 run on
+    // their own streams while the kernels of block b execute (pinned host buffers make the copies truly async)
+    const size_t ncols = (size_t)plan->ncols;
+    const size_t vb = (size_t)n_series * len * sizeof(float), ob = (size_t)n_series * ncols * sizeof(double);
     CK(ctx->values.reserve(vb + 16));
     CK(ctx->out.reserve(std::max<size_t>(ob, 8)));
-    CK(cudaMemcpyAsync(ctx->values.p, values, vb, cudaMemcpyHostToDevice, ctx->stream));
-    R.values = (const float*)ctx->values.p;
-    rc = run_groups(ctx, plan, R, len, (double*)ctx->out.p, flags);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t block = std::max<int64_t>(16384, (n_series + 15) / 16);
+    if (flags & TSFX_FLAG_TIMING) block = n_series;            // per-group events describe one whole pass
+    float* dv = (float*)ctx->values.p;
+    double* dout = (double*)ctx->out.p;
+    int nb = 0;
+    for (int64_t lo = 0; lo < n_series; lo += block, ++nb) {
+        const int64_t cnt = std::min<int64_t>(block, n_series - lo);
+        const int slot = nb & 1;
+        CK(cudaMemcpyAsync(dv + (size_t)lo * len, values + (size_t)lo * len, (size_t)cnt * len * sizeof(float),
+                           cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        R.values = dv + (size_t)lo * len;
+        R.n_series = cnt;
+        rc = run_groups(ctx, plan, R, len, dout + (size_t)lo * ncols, flags);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0));
+        CK(cudaMemcpyAsync(out + (size_t)lo * ncols, dout + (size_t)lo * ncols, (size_t)cnt * ncols * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
     return TSFX_OK;
 }
