@@ -109,12 +109,24 @@ def _cpu_worker(args):
     return m.shape, time.perf_counter() - t0
 
 
+def usable_cores():
+    """host cores this container may actually use: min(affinity mask, cgroup cpu.max quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_baseline(length, name, target_seconds, cores=None):
     """series/s of the CPU path (oracle port of the reference's per-series loop) on all host cores."""
     import multiprocessing as mp
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[k] = "1"          # the reference's own advice, docs/text/tsfresh_on_a_cluster.rst:225-231
-    cores = cores or os.cpu_count() or 1
+    cores = cores or usable_cores()
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         # warm the workers (imports), calibrate on two series per core using the in-worker time, then size the

@@ -1,0 +1,114 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol of include/tsfx.h,
+the plan compiler, roll-window views against the reference's roll_time_series (golden), id-sharding with a
+world_size-2 gloo group."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tsfresh_b200 import _lib
+from tsfresh_b200.plan import CALC, DESC_DTYPE, Plan, param_string
+from tsfresh_b200.settings import ComprehensiveFCParameters
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tsfx.h")).read()
+    declared = set(re.findall(r"\b(tsfx_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().tsfx_version() == 1
+
+
+def test_plan_descriptor_table():
+    p = Plan(ComprehensiveFCParameters())
+    assert p.n_cols == 783 and p.descs.dtype == DESC_DTYPE and p.skipped == ["linear_trend_timewise"]
+    assert list(p.descs["col"]) == list(range(783))
+    i = p.suffixes.index('fft_coefficient__attr_"imag"__coeff_7')
+    assert p.descs[i]["calc"] == CALC["TSFX_FFT_COEFFICIENT"] and p.descs[i]["attr"] == 1 and p.descs[i]["i0"] == 7
+    i = p.suffixes.index("symmetry_looking__r_0.15000000000000002")          # float repr carried into the name
+    assert p.descs[i]["p0"] == 3 * 0.05
+    assert "range_count__max_1000000000000.0__min_0" in p.suffixes
+    assert "cwt_coefficients__coeff_14__w_20__widths_(2, 5, 10, 20)" in p.suffixes
+    tables, off, half = p.cwt_tables()
+    assert list(np.diff(off)) == [34, 82, 162, 322] and list(half) == [16, 40, 80, 160]
+    assert param_string({"b": "x", "a": 1.5}) == 'a_1.5__b_"x"'
+
+
+def test_plan_rejects_what_has_no_gpu_path():
+    with pytest.raises(NotImplementedError):
+        Plan({(lambda x: 0): None})
+    with pytest.raises(NotImplementedError):
+        Plan({"approximate_entropy": [{"m": 3, "r": 0.1}]})
+    with pytest.raises(NotImplementedError):
+        Plan({"query_similarity_count": [{"query": [1.0, 2.0, 3.0], "threshold": 0.0}]})
+    with pytest.raises(AttributeError):
+        Plan({"no_such_calculator": None})
+    with pytest.raises(TypeError):
+        Plan({"quantile": [{"q": 0.5, "extra": 1}]})
+    # per-kind subsets and duplicate-free combiners
+    p = Plan({"ar_coefficient": [{"coeff": 1, "k": 3}, {"coeff": 1, "k": 3}], "maximum": None})
+    assert p.suffixes == ["ar_coefficient__coeff_1__k_3", "maximum"]
+
+
+def test_roll_windows_match_reference_roll_time_series():
+    z = np.load(os.path.join(G, "roll.npz"))
+    lens = z["lens"].astype(np.int32)
+    begin = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    wb, wl, wp, we = _lib.roll_windows(begin, lens, 3, 7, 7)
+    # reference ids are (parent id, time of the window's last row); windows of fewer than 8 rows are dropped
+    got = sorted(zip(wp.tolist(), we.tolist()))
+    want = sorted(zip(z["parent"].tolist(), z["t_end"].tolist()))
+    assert got == want
+    assert set(wl.tolist()) == {8} and set(z["count"].tolist()) == {8}
+    first = {(p, e): b - begin[p] for p, e, b in zip(wp.tolist(), we.tolist(), wb.tolist())}
+    for p, e, f in zip(z["parent"].tolist(), z["t_end"].tolist(), z["first_time"].tolist()):
+        assert first[(p, e)] == f
+    # without min_timeshift the short leading windows are kept too
+    wb, wl, wp, we = _lib.roll_windows(begin, lens, 3, 7, 0)
+    got = {(p, e): l for p, e, l in zip(wp.tolist(), we.tolist(), wl.tolist())}
+    want = {(p, e): c for p, e, c in zip(z["parent_nomin"].tolist(), z["t_end_nomin"].tolist(), z["count_nomin"].tolist())}
+    assert got == want
+    # the benchmark shape of BASELINE.json configs[4]: 121 windows of 256 rows per length-4096 series, stride 32
+    wb, wl, wp, we = _lib.roll_windows(np.array([0, 4096]), np.array([4096, 4096], np.int32), 32, 255, 255)
+    assert len(wb) == 242 and set(wl.tolist()) == {256} and we.max() == 4095
+
+
+def _gloo_worker(rank, world, port, n_rows, q):
+    import torch
+    import torch.distributed as dist
+    from tsfresh_b200 import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full_in = torch.arange(n_rows * 3, dtype=torch.float64).reshape(n_rows, 3)
+    lo, hi = D.shard_bounds(n_rows, world, rank)
+    local = full_in[lo:hi] * 2.0                     # stands in for this rank's extracted rows
+    out = D.gather_rows(local, n_rows)
+    q.put((rank, lo, hi, bool(torch.equal(out, full_in * 2.0))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [10, 7, 1])
+def test_id_sharding_and_gather_world_size_2(n_rows):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_rows, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[3] for r in res] == [True, True]
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == n_rows      # contiguous, covering

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
     float* xs = reinterpret_cast<float*>(hist + nhist);           // npad
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
-    // lock-step walk of the descriptor list per CTA (see k_basic.cu): keeps the instruction working set small
+    // (no lock-step barrier here: measured slower -- the FFT stages dominate and are the same code for every warp)
     for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
         const bool live = (s0 + warp) < A.R.n_series;
         const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
         }
 
         for (int j = 0; j < A.nd; ++j) {
-            if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
