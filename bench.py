@@ -320,7 +320,7 @@ def main():
             for g, cnt in group_columns(plan).items():
                 ncols[g] = cnt
             for g, ms in group_ms.items():
-                by = S * (4 * L + 8 * ncols.get(g, 0))
+                by = S * 16 * F if g == "assemble" else S * (4 * L + 8 * ncols.get(g, 0))
                 groups[g] = {"ms": ms, "columns": ncols.get(g, 0), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
             dom = max(group_ms, key=lambda g: group_ms[g])
             ach = groups[dom]["algorithmic_GBps"]
