@@ -14,6 +14,13 @@
 
 namespace tsfx {
 
+// c += (m <= tau) as DSETP + one predicated IADD (the compiler's own choice is VIADD + predicated MOV)
+__device__ __forceinline__ void count_le(int& c, double m, double tau) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "d"(m), "d"(tau));
+}
+// max of two non-NaN magnitudes without fmax()'s NaN handling (DSETP + SEL instead of DSETP.MAX/FSEL/SEL/LOP3)
+__device__ __forceinline__ double max_nn(double a, double b) { return a > b ? a : b; }
+
 template <int NT>
 __device__ __forceinline__ void entropy_sweep(const double* xd, int n, const double (&tau)[NT], double (&sum_ln2)[NT],
                                               double (&sum_ln3)[NT], double (&sumB)[NT], double (&sumA)[NT], int lane) {
@@ -32,16 +39,16 @@ __device__ __forceinline__ void entropy_sweep(const double* xd, int n, const dou
         double b0 = xd[0], b1 = xd[1];
         for (int j = 0; j < n3; ++j) {
             const double b2 = xd[j + 2];
-            const double m2 = fmax(fabs(a0 - b0), fabs(a1 - b1));
-            const double m3 = fmax(m2, fabs(a2 - b2));
+            const double m2 = max_nn(fabs(a0 - b0), fabs(a1 - b1));
+            const double m3 = max_nn(m2, fabs(a2 - b2));
 #pragma unroll
-            for (int t = 0; t < NT; ++t) { c2[t] += (m2 <= tau[t]); c3[t] += (m3 <= tau[t]); }
+            for (int t = 0; t < NT; ++t) { count_le(c2[t], m2, tau[t]); count_le(c3[t], m3, tau[t]); }
             b0 = b1; b1 = b2;
         }
         {   // last length-2 template j = n2 - 1
-            const double m2 = fmax(fabs(a0 - b0), fabs(a1 - b1));
+            const double m2 = max_nn(fabs(a0 - b0), fabs(a1 - b1));
 #pragma unroll
-            for (int t = 0; t < NT; ++t) c2[t] += (m2 <= tau[t]);
+            for (int t = 0; t < NT; ++t) count_le(c2[t], m2, tau[t]);
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     double* hw = reinterpret_cast<double*>(base + Y.off_hw);
     unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
     short* lines = reinterpret_cast<short*>(base + Y.off_lines);
-    short* colmap = reinterpret_cast<short*>(base + Y.off_map);
+    int* colmap = reinterpret_cast<int*>(base + Y.off_map);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
     const int LCAP = 2 * Y.npad;
@@ -291,92 +291,114 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
                     cwt_ready = true;
                 }
                 const int nrows = d0.i0;
+                // ---- ridge lines (scipy _identify_ridge_lines + _filter_ridge_lines), warp-parallel ----
+                // line table (list order = creation order, as in scipy's Python list)
                 short* l_last = lines;                 // last attached column
                 short* l_gap = lines + LCAP;
                 short* l_len = lines + 2 * LCAP;
                 short* l_minrow = lines + 3 * LCAP;    // smallest row so far
                 short* l_mincol = lines + 4 * LCAP;    // first column attached at that row
+                int* t_max = reinterpret_cast<int*>(lines + 5 * LCAP);   // per-row attachment summaries
+                int* t_min = t_max + LCAP;
+                int* t_cnt = t_min + LCAP;
                 const int min_length = (nrows + 3) / 4;                       // ceil(nrows / 4)
-                // evaluates the filter of _filter_ridge_lines for one finished line
-                auto accept = [&](int li) -> bool {
-                    if (l_len[li] < min_length) return false;
-                    const int rr = l_minrow[li], cc = l_mincol[li];
+                const unsigned lt = (1u << lane) - 1u;
+                const int NONE = 0x7fffffff;
+                int result = 0, nl = 0, start = -1;
+                for (int r = nrows - 1; r >= 0 && start < 0; --r) {             // largest row with any maximum
+                    const unsigned* bits = maxbits + (size_t)r * Y.nwords;
+                    unsigned any = 0;
+                    for (int wd = lane; wd * 32 < n; wd += 32) any |= bits[wd];
+                    if (__any_sync(FULL, any != 0)) start = r;
+                }
+                if (start >= 0) {
+                    const unsigned* bits = maxbits + (size_t)start * Y.nwords;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        const unsigned word = bits[b0 >> 5];
+                        const int idx = nl + __popc(word & lt);
+                        if (((word >> lane) & 1u) && idx < LCAP) {
+                            const int c = b0 + lane;
+                            l_last[idx] = (short)c; l_gap[idx] = 0; l_len[idx] = 1; l_minrow[idx] = (short)start; l_mincol[idx] = (short)c;
+                        }
+                        nl = min(nl + __popc(word), LCAP);
+                    }
+                }
+                __syncwarp();
+                // filter of _filter_ridge_lines for one finished line
+                auto accept = [&](int len, int rr, int cc) -> bool {
+                    if (len < min_length) return false;
                     const double snr = fabs(rows[(size_t)rr * Y.npad + cc] / noise[cc]);
                     return !(snr < 1.0);
                 };
-                int result = 0, nl = 0, start = -1;
-                if (lane == 0) {
-                    // start row: the largest row that has any local maximum; its maxima seed the ridge lines
-                    for (int r = nrows - 1; r >= 0 && start < 0; --r) {
-                        const unsigned* bits = maxbits + (size_t)r * Y.nwords;
-                        for (int wd = 0; wd < Y.nwords; ++wd) if (bits[wd]) { start = r; break; }
-                    }
-                    if (start >= 0) {
-                        const unsigned* bits = maxbits + (size_t)start * Y.nwords;
-                        for (int wd = 0; wd * 32 < n; ++wd) {
-                            unsigned word = bits[wd];
-                            while (word) {
-                                int c = wd * 32 + __ffs(word) - 1;
-                                word &= word - 1;
-                                if (nl < LCAP) { l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)start; l_mincol[nl] = (short)c; ++nl; }
-                            }
-                        }
-                    }
-                }
-                start = __shfl_sync(FULL, start, 0);
                 for (int r = start - 1; r >= 0; --r) {
-                    for (int c = lane; c < n; c += 32) colmap[c] = -1;
+                    const unsigned* bits = maxbits + (size_t)r * Y.nwords;
+                    const int maxd = (r + 1) / 4;                  // floor(widths[r] / 4); distances are integers
+                    for (int c = lane; c < n; c += 32) colmap[c] = NONE;
+                    for (int li = lane; li < nl; li += 32) { t_max[li] = -1; t_min[li] = NONE; t_cnt[li] = 0; l_gap[li] += 1; }
                     __syncwarp();
-                    if (lane == 0) {
-                        const unsigned* bits = maxbits + (size_t)r * Y.nwords;
-                        const int maxd = (r + 1) / 4;                  // floor(widths[r] / 4); distances are integers
-                        // snapshot: column -> first line (list order) whose last column is that column
-                        for (int li = nl - 1; li >= 0; --li) { l_gap[li] += 1; colmap[l_last[li]] = (short)li; }
-                        const int nl_snapshot = nl;
-                        for (int wd = 0; wd * 32 < n; ++wd) {
-                            unsigned word = bits[wd];
-                            while (word) {
-                                const int c = wd * 32 + __ffs(word) - 1;
-                                word &= word - 1;
-                                int best = -1;
-                                if (nl_snapshot > 0) {
-                                    // np.argmin(|c - prev|): the smallest distance wins, first in list order on
-                                    // ties; the point attaches only when that distance is <= max_distances[row]
-                                    for (int dd = 0; dd <= maxd && best < 0; ++dd) {
-                                        int a = (c - dd >= 0) ? colmap[c - dd] : -1;
-                                        int b = (dd > 0 && c + dd < n) ? colmap[c + dd] : -1;
-                                        if (a >= 0 && b >= 0) best = a < b ? a : b;
-                                        else if (a >= 0) best = a;
-                                        else if (b >= 0) best = b;
-                                    }
-                                }
-                                if (best >= 0) {
-                                    l_last[best] = (short)c;
-                                    l_gap[best] = 0;
-                                    l_len[best] += 1;
-                                    if (r < l_minrow[best]) { l_minrow[best] = (short)r; l_mincol[best] = (short)c; }
-                                } else if (nl < LCAP) {
-                                    l_last[nl] = (short)c; l_gap[nl] = 0; l_len[nl] = 1; l_minrow[nl] = (short)r; l_mincol[nl] = (short)c; ++nl;
-                                }
+                    // snapshot: column -> first line (list order) whose last column is that column
+                    for (int li = lane; li < nl; li += 32) atomicMin(&colmap[l_last[li]], li);
+                    __syncwarp();
+                    const int nl_snapshot = nl;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        const unsigned word = bits[b0 >> 5];
+                        const bool mine = (word >> lane) & 1u;
+                        const int c = b0 + lane;
+                        int best = -1;
+                        if (mine && nl_snapshot > 0) {
+                            // np.argmin(|c - prev|): smallest distance, first in list order on ties; attach only
+                            // when that distance is <= max_distances[row]
+                            for (int dd = 0; dd <= maxd && best < 0; ++dd) {
+                                const int a = (c - dd >= 0) ? colmap[c - dd] : NONE;
+                                const int b = (dd > 0 && c + dd < n) ? colmap[c + dd] : NONE;
+                                const int m = min(a, b);
+                                if (m != NONE) best = m;
                             }
                         }
-                        // retire lines whose gap exceeds gap_thresh = ceil(widths[0]) = 1 (order preserved)
-                        int keep = 0;
-                        for (int li = 0; li < nl; ++li) {
-                            if (l_gap[li] > 1) { if (accept(li)) ++result; }
-                            else {
-                                if (keep != li) { l_last[keep] = l_last[li]; l_gap[keep] = l_gap[li]; l_len[keep] = l_len[li]; l_minrow[keep] = l_minrow[li]; l_mincol[keep] = l_mincol[li]; }
-                                ++keep;
-                            }
+                        if (mine && best >= 0) { atomicMax(&t_max[best], c); atomicMin(&t_min[best], c); atomicAdd(&t_cnt[best], 1); }
+                        const unsigned newm = __ballot_sync(FULL, mine && best < 0);
+                        if (mine && best < 0) {
+                            const int idx = nl + __popc(newm & lt);
+                            if (idx < LCAP) { l_last[idx] = (short)c; l_gap[idx] = 0; l_len[idx] = 1; l_minrow[idx] = (short)r; l_mincol[idx] = (short)c; }
                         }
-                        nl = keep;
+                        nl = min(nl + __popc(newm), LCAP);
                     }
                     __syncwarp();
+                    for (int li = lane; li < nl_snapshot; li += 32) {
+                        const int cnt = t_cnt[li];
+                        if (cnt > 0) {      // points are appended in ascending column order within a row
+                            l_last[li] = (short)t_max[li]; l_gap[li] = 0; l_len[li] = (short)(l_len[li] + cnt);
+                            l_minrow[li] = (short)r; l_mincol[li] = (short)t_min[li];
+                        }
+                    }
+                    __syncwarp();
+                    // retire lines whose gap exceeds gap_thresh = ceil(widths[0]) = 1; survivors keep their order
+                    int keep = 0;
+                    for (int b0 = 0; b0 < nl; b0 += 32) {
+                        const int li = b0 + lane;
+                        const bool valid = li < nl;
+                        short f_last = 0, f_gap = 0, f_len = 0, f_row = 0, f_col = 0;
+                        if (valid) { f_last = l_last[li]; f_gap = l_gap[li]; f_len = l_len[li]; f_row = l_minrow[li]; f_col = l_mincol[li]; }
+                        const bool retire = valid && f_gap > 1;
+                        const bool ok = retire && accept(f_len, f_row, f_col);
+                        result += __popc(__ballot_sync(FULL, ok));
+                        const unsigned keepm = __ballot_sync(FULL, valid && !retire);
+                        __syncwarp();
+                        if (valid && !retire) {
+                            const int dst = keep + __popc(keepm & lt);
+                            l_last[dst] = f_last; l_gap[dst] = f_gap; l_len[dst] = f_len; l_minrow[dst] = f_row; l_mincol[dst] = f_col;
+                        }
+                        keep += __popc(keepm);
+                        __syncwarp();
+                    }
+                    nl = keep;
                 }
-                if (lane == 0) {
-                    for (int li = 0; li < nl; ++li) if (accept(li)) ++result;
-                    orow[d0.col] = (double)result;
+                for (int b0 = 0; b0 < nl; b0 += 32) {
+                    const int li = b0 + lane;
+                    const bool ok = li < nl && accept(l_len[li], l_minrow[li], l_mincol[li]);
+                    result += __popc(__ballot_sync(FULL, ok));
                 }
+                if (lane == 0) orow[d0.col] = (double)result;
                 __syncwarp();
                 ++j;
             } else {
@@ -455,8 +477,9 @@ cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm
     Y.off_noise = (int)off; off += (size_t)A.npad * 8;
     Y.off_hw = (int)off;    off += (size_t)TSFX_MAXW_PTS * 8;
     Y.off_bits = (int)off;  off += (size_t)Y.cwt_n * Y.nwords * 4;
-    Y.off_lines = (int)off; off += (size_t)5 * 2 * A.npad * 2;
-    Y.off_map = (int)off;   off += (size_t)A.npad * 2;
+    off = (off + 3) & ~(size_t)3;
+    Y.off_lines = (int)off; off += (size_t)2 * A.npad * (5 * 2 + 3 * 4);      // 5 int16 + 3 int32 tables of 2*npad lines
+    Y.off_map = (int)off;   off += (size_t)A.npad * 4;
     off = (off + 15) & ~(size_t)15;
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
     size_t per = (off + 15) & ~(size_t)15;
