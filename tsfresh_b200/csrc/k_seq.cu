@@ -109,6 +109,42 @@ __device__ __forceinline__ double percentile10(const double* win, int wlen) {
     return (v0 * w0 + v1 * w1) / (w0 + w1);
 }
 
+// ---------------------------------------------------------------------------- permutation patterns
+// A window's rank pattern is fixed by its pairwise order bits b(p,q) = [w_q < w_p], p < q (ties: the earlier
+// sample counts as smaller = stable ranks).  With the bits laid out q-major (bit q(q-1)/2 + p) the pattern of
+// the first D samples is the low D(D-1)/2 bits, so ONE pass over a window serves every dimension.  The dense
+// index used for counting is the Lehmer code: digit p = popcount(bits & PE_MASK[D][p]).
+struct PeMasks { unsigned m[9][8]; };
+__host__ __device__ constexpr PeMasks make_pe_masks() {
+    PeMasks M = {};
+    for (int D = 2; D <= 8; ++D)
+        for (int p = 0; p < D - 1; ++p) {
+            unsigned v = 0;
+            for (int q = p + 1; q < D; ++q) v |= 1u << (q * (q - 1) / 2 + p);
+            M.m[D][p] = v;
+        }
+    return M;
+}
+__constant__ PeMasks PE_MASKS = make_pe_masks();
+
+__device__ __forceinline__ unsigned pe_order_bits(const float* w, int m) {      // m = samples available (<= 8)
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = q < m ? w[q] : 0.f;
+    unsigned bits = 0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+#pragma unroll
+        for (int p = 0; p < q; ++p)
+            if (q < m) bits |= (v[q] < v[p]) ? (1u << (q * (q - 1) / 2 + p)) : 0u;
+    return bits;
+}
+__device__ __forceinline__ unsigned pe_lehmer(unsigned bits, int D) {
+    unsigned code = 0;
+    for (int p = 0; p < D - 1; ++p) code = code * (unsigned)(D - p) + (unsigned)__popc(bits & PE_MASKS.m[D][p]);
+    return code;            // digit D-1 is always 0 (radix 1)
+}
+
 template <int WPC>
 __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,89 +177,118 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                     for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
                 }
                 __syncwarp();
-                // phrase dictionary = prefix-closed trie, stored as an open-addressing hash of (parent, symbol) -> node
-                for (int q = lane; q < cnt * Y.lz_hash; q += 32) trie[(size_t)(q / Y.lz_hash) * Y.lz_stride + (q % Y.lz_hash)] = 0;
+                // phrase dictionary = prefix-closed trie stored as ONE open-addressing table of keys
+                // (parent slot << 16 | symbol); a node's id is the slot its key lives in, the root is 0xffff
+                {
+                    unsigned* tab = reinterpret_cast<unsigned*>(trie);
+                    for (int q = lane; q < cnt * Y.lz_hash; q += 32) tab[q] = 0xffffffffu;
+                }
                 __syncwarp();
                 if (lane < cnt) {
                     const Desc d = A.descs[j + lane];
                     const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
-                    unsigned short* htab = trie + (size_t)lane * Y.lz_stride;         // lz_hash slots, 0 = empty
-                    unsigned short* par = htab + Y.lz_hash;                            // npad + 1
-                    unsigned short* sym = par + (Y.npad + 1);                          // npad + 1
+                    unsigned* hkey = reinterpret_cast<unsigned*>(trie) + (size_t)lane * Y.lz_hash;
                     const unsigned mask = (unsigned)Y.lz_hash - 1u;
-                    int nodes = 1, node = 0, phrases = 0;
+                    unsigned node = 0xffffu;
+                    int phrases = 0;
                     for (int pos = 0; pos < n; ++pos) {
-                        const unsigned sy = sb[pos];
-                        unsigned h = ((unsigned)node * 0x9E3779B1u + sy * 0x85EBCA77u) >> 12;
+                        const unsigned key = (node << 16) | (unsigned)sb[pos];
+                        unsigned h = (key * 0x9E3779B1u) >> 15;
                         h &= mask;
-                        unsigned ch;
-                        while ((ch = htab[h]) != 0u && !(par[ch] == node && sym[ch] == sy)) h = (h + 1u) & mask;
-                        if (ch != 0u) node = (int)ch;
-                        else {
-                            const int nn = nodes++;
-                            par[nn] = (unsigned short)node;
-                            sym[nn] = (unsigned short)sy;
-                            htab[h] = (unsigned short)nn;
-                            ++phrases;
-                            node = 0;
-                        }
+                        unsigned k;
+                        while ((k = hkey[h]) != key && k != 0xffffffffu) h = (h + 1u) & mask;
+                        if (k == key) node = h;                      // phrase seen: extend it
+                        else { hkey[h] = key; ++phrases; node = 0xffffu; }
                     }
                     orow[d.col] = (double)phrases / (double)n;
                 }
                 __syncwarp();
                 j += cnt;
             } else if (d0.calc == TSFX_PERMUTATION_ENTROPY) {
-                const int tau = d0.i0, D = d0.i1;
-                double r = dnan();
-                if (n >= D) {
-                    const int W = (n - D) / tau + 1;
-                    int fact = 1;
-                    for (int q = 2; q <= D; ++q) fact *= q;
-                    // window -> Lehmer index of its rank pattern (ties broken by position: stable order)
-                    auto pattern = [&](int k) -> unsigned {
-                        const float* w = xs + (size_t)k * tau;
-                        unsigned code = 0;
-                        for (int p = 0; p < D; ++p) {
-                            const float wp = w[p];
-                            unsigned c = 0;
-                            for (int q = p + 1; q < D; ++q) c += (w[q] < wp);
-                            code = code * (unsigned)(D - p) + c;
-                        }
-                        return code;
-                    };
-                    double acc = 0.0;
-                    if (fact <= Y.npow2) {
-                        // few patterns: shared-memory histogram over the D! indices
-                        for (int b = lane; b < fact; b += 32) codes[b] = 0u;
-                        __syncwarp();
-                        for (int k = lane; k < W; k += 32) atomicAdd(&codes[pattern(k)], 1u);
-                        __syncwarp();
-                        for (int b = lane; b < fact; b += 32) {
-                            const unsigned c = codes[b];
-                            if (c) { double p = (double)c / (double)W; acc += p * log(p); }
-                        }
-                    } else {
-                        // many patterns: sort the indices and count run lengths
-                        int m = 2;
-                        while (m < W) m <<= 1;
-                        for (int k = lane; k < m; k += 32) codes[k] = (k < W) ? pattern(k) : 0xffffffffu;
-                        __syncwarp();
-                        warp_bitonic_sort_u32(codes, m, lane);
-                        for (int k = lane; k < W; k += 32) {
-                            const unsigned c = codes[k];
-                            if (k == 0 || codes[k - 1] != c) {
-                                int len = 1;
-                                while (k + len < W && codes[k + len] == c) ++len;
-                                double p = (double)len / (double)W;
-                                acc += p * log(p);
-                            }
+                // run of permutation_entropy descriptors sharing tau: one pass over the windows serves all of
+                // them (dimensions <= 6 through shared-memory histograms over the D! Lehmer indices)
+                const int tau = d0.i0;
+                int cnt = 0, bins_total = 0, Dh = 0;
+                while (j + cnt < A.nd && A.descs[j + cnt].calc == TSFX_PERMUTATION_ENTROPY && A.descs[j + cnt].i0 == tau) {
+                    const int D = A.descs[j + cnt].i1;
+                    if (D <= 6) {
+                        int f = 1;
+                        for (int q = 2; q <= D; ++q) f *= q;
+                        if (bins_total + f > Y.npow2) break;
+                        bins_total += f;
+                        Dh = max(Dh, D);
+                    }
+                    ++cnt;
+                }
+                if (Dh > 0) {
+                    for (int b = lane; b < bins_total; b += 32) codes[b] = 0u;
+                    __syncwarp();
+                    const int Wmax = (n >= 2) ? (n - 2) / tau + 1 : 0;          // windows of the smallest dimension
+                    for (int k = lane; k < Wmax; k += 32) {
+                        const int st = k * tau;
+                        const unsigned bits = pe_order_bits(xs + st, min(8, n - st));
+                        int off = 0;
+                        for (int t = 0; t < cnt; ++t) {
+                            const int D = A.descs[j + t].i1;
+                            if (D > 6) continue;
+                            int f = 1;
+                            for (int q = 2; q <= D; ++q) f *= q;
+                            if (st + D <= n) atomicAdd(&codes[off + pe_lehmer(bits, D)], 1u);
+                            off += f;
                         }
                     }
-                    r = -wsum(acc);
+                    __syncwarp();
+                    int off = 0;
+                    for (int t = 0; t < cnt; ++t) {
+                        const Desc d = A.descs[j + t];
+                        const int D = d.i1;
+                        if (D > 6) continue;
+                        int f = 1;
+                        for (int q = 2; q <= D; ++q) f *= q;
+                        double r = dnan();
+                        if (n >= D) {
+                            const int W = (n - D) / tau + 1;
+                            // -sum p ln p = ln W - (1/W) sum c ln c  (bins with c = 1 contribute nothing)
+                            double acc = 0.0;
+                            for (int b = lane; b < f; b += 32) {
+                                const unsigned c = codes[off + b];
+                                if (c > 1u) acc += (double)c * log((double)c);
+                            }
+                            r = log((double)W) - wsum(acc) / (double)W;
+                        }
+                        if (lane == 0) orow[d.col] = r;
+                        off += f;
+                    }
                     __syncwarp();
                 }
-                if (lane == 0) orow[d0.col] = r;
-                ++j;
+                for (int t = 0; t < cnt; ++t) {             // dimensions 7, 8: sort the indices, count run lengths
+                    const Desc d = A.descs[j + t];
+                    const int D = d.i1;
+                    if (D <= 6) continue;
+                    double r = dnan();
+                    if (n >= D) {
+                        const int W = (n - D) / tau + 1;
+                        int m = 2;
+                        while (m < W) m <<= 1;
+                        for (int k = lane; k < m; k += 32)
+                            codes[k] = (k < W) ? pe_lehmer(pe_order_bits(xs + k * tau, D), D) : 0xffffffffu;
+                        __syncwarp();
+                        warp_bitonic_sort_u32(codes, m, lane);
+                        double acc = 0.0;
+                        for (int k = lane; k < W; k += 32) {
+                            const unsigned c = codes[k];
+                            if ((k == 0 || codes[k - 1] != c) && k + 1 < W && codes[k + 1] == c) {
+                                int len = 2;
+                                while (k + len < W && codes[k + len] == c) ++len;
+                                acc += (double)len * log((double)len);
+                            }
+                        }
+                        r = log((double)W) - wsum(acc) / (double)W;
+                        __syncwarp();
+                    }
+                    if (lane == 0) orow[d.col] = r;
+                }
+                j += cnt;
             } else {
                 if (lane == 0) orow[d0.col] = dnan();
                 ++j;
@@ -430,7 +495,7 @@ static void seq_geometry(size_t per, int sm_count, int64_t n_series, int* wpc_ou
 cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     SeqArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    if (max_len > 32000) return cudaErrorInvalidConfiguration;
+    if (max_len > 21000) return cudaErrorInvalidConfiguration;      // LZ node ids are 15-bit slot indices
     SeqLayout Y = {};
     Y.npad = A.npad;
     int p2 = 2;
@@ -439,8 +504,8 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     const bool need_lz = (A.nscr & 1) != 0, need_perm = (A.nscr & 2) != 0;
     Y.lz_lanes = need_lz ? std::min(LZ_LANES, std::max(1, (A.nscr >> 16) & 0xff)) : 0;
     Y.lz_hash = 4;
-    while (Y.lz_hash < A.npad + 2) Y.lz_hash <<= 1;
-    Y.lz_stride = Y.lz_hash + 2 * (A.npad + 1);
+    while (Y.lz_hash < A.npad + A.npad / 2 + 2) Y.lz_hash <<= 1;      // load factor <= 2/3 in the worst case
+    Y.lz_stride = 2 * Y.lz_hash;                  // uint16 units: one uint32 key per slot
     size_t off = 0;
     Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
     Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * Y.lz_stride * 2;
