@@ -110,3 +110,23 @@ def test_duplicate_timestamps_are_stable():
     df = pd.DataFrame({"id": [1, 1, 1, 0, 0], "time": [5, 5, 1, 2, 2], "value": np.float32([3, 4, 9, 7, 8])})
     X = extract_features(df, column_id="id", column_sort="time", default_fc_parameters={"mean_change": None})
     assert X.loc[1, "value__mean_change"] == (4 - 9) / 2 and X.loc[0, "value__mean_change"] == 1.0
+
+
+def test_rolled_windows_as_views_match_oracle_on_materialised_windows():
+    """BASELINE.json configs[4] path: roll_time_series(win, stride) windows are (begin, len) views over the one
+    value buffer (tsfx_roll_windows, checked against the reference's window ids in tests/test_host_side.py);
+    extracting the views must equal the oracle on the copied-out windows."""
+    from tests.helpers import to_csr
+    from tsfresh_b200 import _lib
+    from tsfresh_b200.extraction import _device_plan, get_context
+    series = list(synthetic_series(9, 3, 200)) + [synthetic_series(10, 1, 77)[0]]
+    values, begin, lens = to_csr(series)
+    wb, wl, wp, we = _lib.roll_windows(begin, lens, 32, 63, 63)         # windows of 64 rows, stride 32
+    assert len(wb) == 3 * 5 + 1 and set(wl.tolist()) == {64}
+    settings = EfficientFCParameters()
+    plan = Plan(settings)
+    dp = _device_plan(get_context(0), plan)
+    got = dp.extract_csr(values, wb, wl)
+    windows = [values[b:b + n].astype(np.float64) for b, n in zip(wb, wl)]
+    bad = compare(got, oracle_rows(windows, settings), plan.suffixes)
+    assert not bad, bad[:20]

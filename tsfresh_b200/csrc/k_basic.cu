@@ -238,6 +238,100 @@ __device__ __forceinline__ int leading_digit(float f, const double* dec) {
     return d;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "Finisher" calculators are O(1) functions of the shared per-series statistics.  The statistics are parked
+// in shared memory (ST) and the finishers are evaluated LANE-PARALLEL (lane l takes descriptors l, l+32, ...),
+// so ~70 of the 178 BASIC columns cost a couple of warp instructions each instead of a full trip through
+// the warp-uniform descriptor loop.
+enum { ST_N = 0, ST_SUM, ST_MEAN, ST_SUMSQ, ST_M2, ST_VAR, ST_SD, ST_MIN, ST_MAX, ST_M3, ST_M4, ST_SAD, ST_SSD,
+       ST_CNT_ABOVE, ST_CNT_BELOW, ST_CNT_MIN, ST_CNT_MAX, ST_FIRST_MIN, ST_LAST_MIN, ST_FIRST_MAX, ST_LAST_MAX,
+       ST_STRIKE_ABOVE, ST_STRIKE_BELOW, ST_X0, ST_X1, ST_XN2, ST_XN1, ST_COUNT };
+
+__host__ __device__ inline bool basic_is_finisher(int calc) {
+    switch (calc) {
+        case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: case TSFX_LARGE_STANDARD_DEVIATION:
+        case TSFX_HAS_DUPLICATE_MAX: case TSFX_HAS_DUPLICATE_MIN: case TSFX_SUM_VALUES: case TSFX_ABS_ENERGY:
+        case TSFX_MEAN: case TSFX_LENGTH: case TSFX_STANDARD_DEVIATION: case TSFX_VARIANCE:
+        case TSFX_VARIATION_COEFFICIENT: case TSFX_ROOT_MEAN_SQUARE: case TSFX_MAXIMUM: case TSFX_MINIMUM:
+        case TSFX_ABSOLUTE_MAXIMUM: case TSFX_MEAN_ABS_CHANGE: case TSFX_ABSOLUTE_SUM_OF_CHANGES:
+        case TSFX_MEAN_CHANGE: case TSFX_MEAN_SECOND_DERIVATIVE_CENTRAL: case TSFX_SKEWNESS: case TSFX_KURTOSIS:
+        case TSFX_LONGEST_STRIKE_BELOW_MEAN: case TSFX_LONGEST_STRIKE_ABOVE_MEAN: case TSFX_COUNT_ABOVE_MEAN:
+        case TSFX_COUNT_BELOW_MEAN: case TSFX_LAST_LOCATION_OF_MAXIMUM: case TSFX_FIRST_LOCATION_OF_MAXIMUM:
+        case TSFX_LAST_LOCATION_OF_MINIMUM: case TSFX_FIRST_LOCATION_OF_MINIMUM: case TSFX_CID_CE:
+        case TSFX_AUTOCORRELATION: case TSFX_QUERY_SIMILARITY_COUNT: case TSFX_CONST_NAN:
+            return true;
+        default:
+            return false;
+    }
+}
+
+__device__ __noinline__ double basic_finisher(const Desc& d, const double* ST, const double* lagS) {
+    const double dn = ST[ST_N];
+    const int n = (int)dn;
+    switch (d.calc) {
+        case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: return (ST[ST_VAR] > sqrt(ST[ST_VAR])) ? 1.0 : 0.0;
+        case TSFX_LARGE_STANDARD_DEVIATION: return (ST[ST_SD] > d.p0 * (ST[ST_MAX] - ST[ST_MIN])) ? 1.0 : 0.0;
+        case TSFX_HAS_DUPLICATE_MAX: return ST[ST_CNT_MAX] >= 2.0 ? 1.0 : 0.0;
+        case TSFX_HAS_DUPLICATE_MIN: return ST[ST_CNT_MIN] >= 2.0 ? 1.0 : 0.0;
+        case TSFX_SUM_VALUES: return ST[ST_SUM];
+        case TSFX_ABS_ENERGY: return ST[ST_SUMSQ];
+        case TSFX_MEAN: return ST[ST_MEAN];
+        case TSFX_LENGTH: return dn;
+        case TSFX_STANDARD_DEVIATION: return ST[ST_SD];
+        case TSFX_VARIANCE: return ST[ST_VAR];
+        case TSFX_VARIATION_COEFFICIENT: return (ST[ST_MEAN] != 0.0) ? ST[ST_SD] / ST[ST_MEAN] : dnan();
+        case TSFX_ROOT_MEAN_SQUARE: return sqrt(ST[ST_SUMSQ] / dn);
+        case TSFX_MAXIMUM: return ST[ST_MAX];
+        case TSFX_MINIMUM: return ST[ST_MIN];
+        case TSFX_ABSOLUTE_MAXIMUM: return fmax(fabs(ST[ST_MIN]), fabs(ST[ST_MAX]));
+        case TSFX_MEAN_ABS_CHANGE: return ST[ST_SAD] / (double)(n - 1);
+        case TSFX_ABSOLUTE_SUM_OF_CHANGES: return ST[ST_SAD];
+        case TSFX_MEAN_CHANGE: return n > 1 ? (ST[ST_XN1] - ST[ST_X0]) / (double)(n - 1) : dnan();
+        case TSFX_MEAN_SECOND_DERIVATIVE_CENTRAL:
+            return n > 2 ? (ST[ST_XN1] - ST[ST_XN2] - ST[ST_X1] + ST[ST_X0]) / (2.0 * (double)(n - 2)) : dnan();
+        case TSFX_SKEWNESS: {   // pandas nanops.nanskew
+            double amax = fmax(fabs(ST[ST_MIN]), fabs(ST[ST_MAX]));
+            double e1 = 2.220446049250313e-16 * amax;
+            double m2 = ST[ST_M2], m3 = ST[ST_M3];
+            if (fabs(m2) < e1 * e1 * dn) m2 = 0.0;
+            if (fabs(m3) < e1 * e1 * e1 * dn) m3 = 0.0;
+            if (n < 3) return dnan();
+            if (m2 == 0.0) return 0.0;
+            return (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2)));
+        }
+        case TSFX_KURTOSIS: {   // pandas nanops.nankurt
+            double amax = fmax(fabs(ST[ST_MIN]), fabs(ST[ST_MAX]));
+            double e1 = 2.220446049250313e-16 * amax, e2 = e1 * e1;
+            double m2 = ST[ST_M2], m4 = ST[ST_M4];
+            if (fabs(m2) < e2 * dn) m2 = 0.0;
+            if (fabs(m4) < e2 * e2 * dn) m4 = 0.0;
+            if (n < 4) return dnan();
+            double adj = 3.0 * (dn - 1.0) * (dn - 1.0) / ((dn - 2.0) * (dn - 3.0));
+            double num = dn * (dn + 1.0) * (dn - 1.0) * m4;
+            double den = (dn - 2.0) * (dn - 3.0) * m2 * m2;
+            return (den == 0.0) ? 0.0 : num / den - adj;
+        }
+        case TSFX_LONGEST_STRIKE_BELOW_MEAN: return ST[ST_STRIKE_BELOW];
+        case TSFX_LONGEST_STRIKE_ABOVE_MEAN: return ST[ST_STRIKE_ABOVE];
+        case TSFX_COUNT_ABOVE_MEAN: return ST[ST_CNT_ABOVE];
+        case TSFX_COUNT_BELOW_MEAN: return ST[ST_CNT_BELOW];
+        case TSFX_LAST_LOCATION_OF_MAXIMUM: return 1.0 - (double)(n - 1 - (int)ST[ST_LAST_MAX]) / dn;
+        case TSFX_FIRST_LOCATION_OF_MAXIMUM: return ST[ST_FIRST_MAX] / dn;
+        case TSFX_LAST_LOCATION_OF_MINIMUM: return 1.0 - (double)(n - 1 - (int)ST[ST_LAST_MIN]) / dn;
+        case TSFX_FIRST_LOCATION_OF_MINIMUM: return ST[ST_FIRST_MIN] / dn;
+        case TSFX_CID_CE:
+            if (d.i0) return (ST[ST_SD] != 0.0) ? sqrt(ST[ST_SSD]) / ST[ST_SD] : 0.0;
+            return sqrt(ST[ST_SSD]);
+        case TSFX_AUTOCORRELATION: {
+            const int lag = d.i0;
+            if (n < lag || ST[ST_VAR] <= 1e-8) return dnan();      // np.isclose(v, 0) with v >= 0
+            if (lag >= n) return dnan();                            // 0 / 0
+            return lagS[lag] / ((double)(n - lag) * ST[ST_VAR]);
+        }
+        default: return dnan();
+    }
+}
+
 template <int WPC>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -246,7 +340,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
     double* xc = reinterpret_cast<double*>(base);
     double* scr = xc + A.npad;
     double* lagS = scr + A.nscr;
-    float* xs = reinterpret_cast<float*>(lagS + A.nlag);
+    double* ST = lagS + A.nlag;                     // ST_COUNT (padded to 32) shared statistics
+    float* xs = reinterpret_cast<float*>(ST + 32);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
     // The kernel body is ~250 KB of SASS; warps drifting through different calculators thrash the
@@ -270,79 +365,34 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
             }
             __syncwarp();
         }
+        if (lane == 0) {
+            ST[ST_N] = dn; ST[ST_SUM] = M.sum; ST[ST_MEAN] = M.mean; ST[ST_SUMSQ] = M.sumsq; ST[ST_M2] = M.m2;
+            ST[ST_VAR] = M.var; ST[ST_SD] = M.sd; ST[ST_MIN] = M.vmin; ST[ST_MAX] = M.vmax; ST[ST_M3] = E.m3;
+            ST[ST_M4] = E.m4; ST[ST_SAD] = E.sad; ST[ST_SSD] = E.ssd; ST[ST_CNT_ABOVE] = (double)E.cnt_above;
+            ST[ST_CNT_BELOW] = (double)E.cnt_below; ST[ST_CNT_MIN] = (double)E.cnt_min; ST[ST_CNT_MAX] = (double)E.cnt_max;
+            ST[ST_FIRST_MIN] = (double)E.first_min; ST[ST_LAST_MIN] = (double)E.last_min;
+            ST[ST_FIRST_MAX] = (double)E.first_max; ST[ST_LAST_MAX] = (double)E.last_max;
+            ST[ST_STRIKE_ABOVE] = (double)E.strike_above; ST[ST_STRIKE_BELOW] = (double)E.strike_below;
+            ST[ST_X0] = (double)xs[0]; ST[ST_X1] = (double)xs[n > 1 ? 1 : 0];
+            ST[ST_XN2] = (double)xs[n > 1 ? n - 2 : 0]; ST[ST_XN1] = (double)xs[n - 1];
+        }
+        __syncwarp();
+        // finishers (the first A.nfin descriptors of the group): one descriptor per lane
+        if (live)
+            for (int j = lane; j < A.nfin; j += 32) {
+                const Desc d = A.descs[j];
+                orow[d.col] = basic_finisher(d, ST, lagS);
+            }
         // caches for multi-column calculators
         int lt_key = -1; LinReg lt_fit;
         bool lin_done = false; LinReg lin_fit;
         bool pacf_done = false, peaks_done = false;
 
-        for (int j = 0; j < A.nd; ++j) {
+        for (int j = A.nfin; j < A.nd; ++j) {
             if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
-                case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: r = (M.var > sqrt(M.var)) ? 1.0 : 0.0; break;
-                case TSFX_LARGE_STANDARD_DEVIATION: r = (M.sd > d.p0 * (M.vmax - M.vmin)) ? 1.0 : 0.0; break;
-                case TSFX_HAS_DUPLICATE_MAX: r = E.cnt_max >= 2 ? 1.0 : 0.0; break;
-                case TSFX_HAS_DUPLICATE_MIN: r = E.cnt_min >= 2 ? 1.0 : 0.0; break;
-                case TSFX_SUM_VALUES: r = M.sum; break;
-                case TSFX_ABS_ENERGY: r = M.sumsq; break;
-                case TSFX_MEAN: r = M.mean; break;
-                case TSFX_LENGTH: r = dn; break;
-                case TSFX_STANDARD_DEVIATION: r = M.sd; break;
-                case TSFX_VARIANCE: r = M.var; break;
-                case TSFX_VARIATION_COEFFICIENT: r = (M.mean != 0.0) ? M.sd / M.mean : dnan(); break;
-                case TSFX_ROOT_MEAN_SQUARE: r = sqrt(M.sumsq / dn); break;
-                case TSFX_MAXIMUM: r = M.vmax; break;
-                case TSFX_MINIMUM: r = M.vmin; break;
-                case TSFX_ABSOLUTE_MAXIMUM: r = fmax(fabs(M.vmin), fabs(M.vmax)); break;
-                case TSFX_MEAN_ABS_CHANGE: r = E.sad / (double)(n - 1); break;
-                case TSFX_ABSOLUTE_SUM_OF_CHANGES: r = E.sad; break;
-                case TSFX_MEAN_CHANGE:
-                    r = n > 1 ? ((double)xs[n - 1] - (double)xs[0]) / (double)(n - 1) : dnan();
-                    break;
-                case TSFX_MEAN_SECOND_DERIVATIVE_CENTRAL:
-                    r = n > 2 ? ((double)xs[n - 1] - (double)xs[n - 2] - (double)xs[1] + (double)xs[0]) /
-                                    (2.0 * (double)(n - 2))
-                              : dnan();
-                    break;
-                case TSFX_SKEWNESS: {   // pandas nanops.nanskew
-                    double amax = fmax(fabs(M.vmin), fabs(M.vmax));
-                    double e1 = 2.220446049250313e-16 * amax;
-                    double m2 = M.m2, m3 = E.m3;
-                    if (fabs(m2) < e1 * e1 * dn) m2 = 0.0;
-                    if (fabs(m3) < e1 * e1 * e1 * dn) m3 = 0.0;
-                    if (n < 3) r = dnan();
-                    else if (m2 == 0.0) r = 0.0;
-                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2)));
-                    break;
-                }
-                case TSFX_KURTOSIS: {   // pandas nanops.nankurt
-                    double amax = fmax(fabs(M.vmin), fabs(M.vmax));
-                    double e1 = 2.220446049250313e-16 * amax, e2 = e1 * e1;
-                    double m2 = M.m2, m4 = E.m4;
-                    if (fabs(m2) < e2 * dn) m2 = 0.0;
-                    if (fabs(m4) < e2 * e2 * dn) m4 = 0.0;
-                    if (n < 4) r = dnan();
-                    else {
-                        double adj = 3.0 * (dn - 1.0) * (dn - 1.0) / ((dn - 2.0) * (dn - 3.0));
-                        double num = dn * (dn + 1.0) * (dn - 1.0) * m4;
-                        double den = (dn - 2.0) * (dn - 3.0) * m2 * m2;
-                        r = (den == 0.0) ? 0.0 : num / den - adj;
-                    }
-                    break;
-                }
-                case TSFX_LONGEST_STRIKE_BELOW_MEAN: r = (double)E.strike_below; break;
-                case TSFX_LONGEST_STRIKE_ABOVE_MEAN: r = (double)E.strike_above; break;
-                case TSFX_COUNT_ABOVE_MEAN: r = (double)E.cnt_above; break;
-                case TSFX_COUNT_BELOW_MEAN: r = (double)E.cnt_below; break;
-                case TSFX_LAST_LOCATION_OF_MAXIMUM: r = 1.0 - (double)(n - 1 - E.last_max) / dn; break;
-                case TSFX_FIRST_LOCATION_OF_MAXIMUM: r = (double)E.first_max / dn; break;
-                case TSFX_LAST_LOCATION_OF_MINIMUM: r = 1.0 - (double)(n - 1 - E.last_min) / dn; break;
-                case TSFX_FIRST_LOCATION_OF_MINIMUM: r = (double)E.first_min / dn; break;
-                case TSFX_CID_CE:
-                    if (d.i0) r = (M.sd != 0.0) ? sqrt(E.ssd) / M.sd : 0.0;
-                    else r = sqrt(E.ssd);
-                    break;
                 case TSFX_RATIO_BEYOND_R_SIGMA: {
                     double thr = d.p0 * M.sd;
                     int c = 0;
@@ -423,13 +473,6 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
                         }
                     }
                     r = (double)c;
-                    break;
-                }
-                case TSFX_AUTOCORRELATION: {
-                    int lag = d.i0;
-                    if (n < lag || M.var <= 1e-8) r = dnan();      // np.isclose(v, 0) with v >= 0
-                    else if (lag >= n) r = dnan();                  // 0 / 0
-                    else r = lagS[lag] / ((double)(n - lag) * M.var);
                     break;
                 }
                 case TSFX_AGG_AUTOCORRELATION: {
@@ -614,11 +657,13 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArg
     }
 }
 
+bool basic_finisher_calc(int calc) { return basic_is_finisher(calc); }
+
 // ------------------------------------------------------------------------------------------ launcher
 cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     BasicArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    size_t per = (size_t)A.npad * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + (size_t)A.npad * 4;
+    size_t per = (size_t)A.npad * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + 32 * 8 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     int wpc = (int)(100 * 1024 / per);

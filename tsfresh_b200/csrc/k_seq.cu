@@ -19,7 +19,7 @@ namespace tsfx {
 
 struct SeqLayout {
     int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride;
-    int off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs;   // byte offsets
+    int off_rowsf, off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs;   // byte offsets
 };
 
 // ---------------------------------------------------------------------------- Lempel-Ziv
@@ -303,15 +303,17 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
-    double* rows = reinterpret_cast<double*>(base);                       // cwt_n x npad
-    double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad
+    double* row0 = reinterpret_cast<double*>(base);                       // npad : width-1 row (float64)
+    double* tmp = row0 + Y.npad;                                           // npad : the row being formed
+    double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad : memoised noise floor (NaN = not yet)
+    float* rowsf = reinterpret_cast<float*>(base + Y.off_rowsf);           // (cwt_n - 1) x npad : wider rows, float32 copies
     double* hw = reinterpret_cast<double*>(base + Y.off_hw);
     unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
     short* lines = reinterpret_cast<short*>(base + Y.off_lines);
     int* colmap = reinterpret_cast<int*>(base + Y.off_map);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
-    const int LCAP = 2 * Y.npad;
+    const int LCAP = Y.npad + Y.npad / 2 + 32;   // alive (<= maxima of the two previous rows <= n) + new in this row (<= n/2)
 
     for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
         const int n = load_series(A.R, s, xs, lane);
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
                     for (int w = 1; w <= Y.cwt_n; ++w) {
                         const int npts = min(10 * w, n);
                         ricker_fill(hw, npts, w, lane);
-                        double* dst = rows + (size_t)(w - 1) * Y.npad;
+                        double* dst = (w == 1) ? row0 : tmp;
                         for (int i = lane; i < n; i += 32) dst[i] = cwt_value(xs, n, hw, npts, i);
                         __syncwarp();
                         unsigned* bits = maxbits + (size_t)(w - 1) * Y.nwords;
@@ -338,21 +340,15 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
                                 double v = dst[i];
                                 double pl = dst[min(i + 1, n - 1)], mi = dst[max(i - 1, 0)];
                                 mx = (v > pl) && (v > mi);
+                                if (w > 1) rowsf[(size_t)(w - 2) * Y.npad + i] = (float)v;   // only read for the SNR test
                             }
                             unsigned word = __ballot_sync(FULL, mx);
                             if (lane == 0) bits[b0 >> 5] = word;
                         }
                         __syncwarp();
                     }
-                    // noise floor of _filter_ridge_lines for every column: 10th percentile of row 0 in a window
-                    {
-                        const int window = (n + 19) / 20, hf = window / 2, odd = window & 1;
-                        for (int c = lane; c < n; c += 32) {
-                            const int ws = max(c - hf, 0), we = min(c + hf + odd, n);
-                            noise[c] = percentile10(rows + ws, we - ws);
-                        }
-                        __syncwarp();
-                    }
+                    for (int c = lane; c < n; c += 32) noise[c] = dnan();
+                    __syncwarp();
                     cwt_ready = true;
                 }
                 const int nrows = d0.i0;
@@ -390,9 +386,17 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
                 }
                 __syncwarp();
                 // filter of _filter_ridge_lines for one finished line
+                const int window = (n + 19) / 20, hf = window / 2, odd = window & 1;
                 auto accept = [&](int len, int rr, int cc) -> bool {
                     if (len < min_length) return false;
-                    const double snr = fabs(rows[(size_t)rr * Y.npad + cc] / noise[cc]);
+                    double nz = noise[cc];
+                    if (nz != nz) {                 // 10th percentile of row 0 around cc, formed on first use
+                        const int ws = max(cc - hf, 0), we = min(cc + hf + odd, n);
+                        nz = percentile10(row0 + ws, we - ws);
+                        noise[cc] = nz;
+                    }
+                    const double val = (rr == 0) ? row0[cc] : (double)rowsf[(size_t)(rr - 1) * Y.npad + cc];
+                    const double snr = fabs(val / nz);
                     return !(snr < 1.0);
                 };
                 for (int r = start - 1; r >= 0; --r) {
@@ -538,12 +542,13 @@ cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm
     Y.nwords = (A.npad + 31) / 32 + 1;
     Y.cwt_n = (A.nscr >> 8) & 0xff;
     size_t off = 0;
-    off += (size_t)Y.cwt_n * A.npad * 8;                    // rows
+    off += (size_t)2 * A.npad * 8;                          // row0 + tmp (float64)
     Y.off_noise = (int)off; off += (size_t)A.npad * 8;
     Y.off_hw = (int)off;    off += (size_t)TSFX_MAXW_PTS * 8;
     Y.off_bits = (int)off;  off += (size_t)Y.cwt_n * Y.nwords * 4;
     off = (off + 3) & ~(size_t)3;
-    Y.off_lines = (int)off; off += (size_t)2 * A.npad * (5 * 2 + 3 * 4);      // 5 int16 + 3 int32 tables of 2*npad lines
+    Y.off_rowsf = (int)off; off += (size_t)std::max(Y.cwt_n - 1, 0) * A.npad * 4;
+    Y.off_lines = (int)off; off += (size_t)(A.npad + A.npad / 2 + 32) * (5 * 2 + 3 * 4);    // 5 int16 + 3 int32 tables of LCAP lines
     Y.off_map = (int)off;   off += (size_t)A.npad * 4;
     off = (off + 15) & ~(size_t)15;
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;

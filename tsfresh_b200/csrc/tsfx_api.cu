@@ -57,6 +57,7 @@ struct tsfx_plan {
     std::vector<Desc> host[G_COUNT];
     Desc* dev[G_COUNT] = {nullptr};
     int32_t* d_final_col = nullptr;   // final column of every staged column, groups concatenated
+    int basic_nfin = 0;               // leading "finisher" descriptors of the BASIC group
     int cum[G_COUNT + 1] = {0};
     int ncols = 0;
     int lag_needed = 0, pacf_want = -1;
@@ -247,7 +248,11 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
     if (P->lag_needed > 4096) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "lag > 4096"); }
     std::vector<int32_t> final_col;
     for (int g = 0; g < G_COUNT; ++g) {
-        std::stable_sort(P->host[g].begin(), P->host[g].end(), [](const Desc& a, const Desc& b) {
+        std::stable_sort(P->host[g].begin(), P->host[g].end(), [g](const Desc& a, const Desc& b) {
+            if (g == G_BASIC) {               // O(1) finishers first (evaluated lane-parallel)
+                const bool fa = basic_finisher_calc(a.calc), fb = basic_finisher_calc(b.calc);
+                if (fa != fb) return fa;
+            }
             if (a.calc != b.calc) return a.calc < b.calc;
             if (a.i1 != b.i1) return a.i1 < b.i1;
             if (a.i2 != b.i2) return a.i2 < b.i2;
@@ -256,6 +261,8 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
             if (a.i0 != b.i0) return a.i0 < b.i0;
             return a.col < b.col;
         });
+        if (g == G_BASIC)
+            for (const Desc& d : P->host[g]) P->basic_nfin += basic_finisher_calc(d.calc) ? 1 : 0;
         P->cum[g + 1] = P->cum[g] + (int)P->host[g].size();
         for (size_t j = 0; j < P->host[g].size(); ++j) {      // col becomes the index inside the group's staging row
             final_col.push_back(P->host[g][j].col);
@@ -340,6 +347,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 BasicArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.lag_needed = P->lag_needed;
+                A.nfin = P->basic_nfin;
                 int pac = P->pacf_want >= 0 ? 4 * (P->pacf_want + 1) : 0;
                 A.pacf_off = P->lag_needed + 1;
                 A.nlag = even(P->lag_needed + 1 + pac);

@@ -32,11 +32,13 @@ struct BasicArgs {
     double* out;
     int ncols;
     int npad, nscr, nlag, bytes_per_warp;   // shared-memory carve-up (doubles / doubles / doubles / bytes)
+    int nfin;            // the first nfin descriptors are O(1) "finishers" (see k_basic.cu)
     int lag_needed;      // largest lag product any descriptor reads (0 = none)
     int pacf_off;        // offset (doubles) of the pacf staging area inside lagS
     const double* dec;   // device table d*10^k, k = TSFX_DEC_MIN..TSFX_DEC_MAX, 9 per decade
 };
 cudaError_t launch_basic(const BasicArgs& A, int max_len, cudaStream_t st, int sm_count);
+bool basic_finisher_calc(int calc);     // host: is this calculator evaluated by the lane-parallel finisher stage?
 
 struct SortedArgs {
     SeriesRef R;
