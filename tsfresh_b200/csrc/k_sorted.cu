@@ -73,6 +73,63 @@ __device__ __forceinline__ double quantile_view(const DropLast& v, int n, double
     return a + d * t;
 }
 
+// np.polyfit(x, y, 3) for k >= 4 points held in shared memory, all lanes cooperating (points strided over
+// lanes): column-scaled normal equations, 4x4 Cholesky done redundantly by every lane, two refinement steps
+// with residuals formed from the data (same algebra as m_polyfit3, which stays for the k < 4 minimum-norm case).
+__device__ __forceinline__ bool warp_polyfit3(const double* x, const double* y, int k, double* coef, int lane) {
+    double sc[4] = {0, 0, 0, 0};
+    for (int i = lane; i < k; i += 32) {
+        const double v = x[i], v2 = v * v, v3 = v2 * v;
+        sc[0] = fma(v3, v3, sc[0]); sc[1] = fma(v2, v2, sc[1]); sc[2] = fma(v, v, sc[2]); sc[3] += 1.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sc[a] = sqrt(wsum(sc[a]));
+    double G[16], rhs[4];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) G[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rhs[a] = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double v = x[i];
+        const double col[4] = {v * v * v / sc[0], v * v / sc[1], v / sc[2], 1.0 / sc[3]};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            rhs[a] = fma(col[a], y[i], rhs[a]);
+#pragma unroll
+            for (int b = 0; b <= a; ++b) G[a * 4 + b] = fma(col[a], col[b], G[a * 4 + b]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        rhs[a] = wsum(rhs[a]);
+#pragma unroll
+        for (int b = 0; b <= a; ++b) G[a * 4 + b] = wsum(G[a * 4 + b]);
+    }
+    if (!m_cholesky(G, 4, 4)) return false;
+    double sol[4] = {rhs[0], rhs[1], rhs[2], rhs[3]};
+    m_forward(G, 4, 4, sol);
+    m_backward(G, 4, 4, sol);
+    for (int it = 0; it < 2; ++it) {
+        double r4[4] = {0, 0, 0, 0};
+        for (int i = lane; i < k; i += 32) {
+            const double v = x[i];
+            const double col[4] = {v * v * v / sc[0], v * v / sc[1], v / sc[2], 1.0 / sc[3]};
+            const double e = y[i] - (col[0] * sol[0] + col[1] * sol[1] + col[2] * sol[2] + col[3] * sol[3]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) r4[a] = fma(col[a], e, r4[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) r4[a] = wsum(r4[a]);
+        m_forward(G, 4, 4, r4);
+        m_backward(G, 4, 4, r4);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) sol[a] += r4[a];
+    }
+    if (lane == 0) { coef[0] = sol[0] / sc[0]; coef[1] = sol[1] / sc[1]; coef[2] = sol[2] / sc[2]; coef[3] = sol[3] / sc[3]; }
+    __syncwarp();
+    return true;
+}
+
 // Estimates the Friedrich cubic (feature_calculators.py:131-173 with m = 3): returns in all lanes
 // whether a coefficient vector exists; coefficients land in coef[0..3] (shared memory).
 __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt, int n, int r, double* scr, double* coef,
@@ -119,18 +176,25 @@ __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt,
         }
     }
     __syncwarp();
-    int ok = 0;
+    int k = 0;
     if (lane == 0) {
-        int k = 0;
         for (int b = 0; b < r; ++b) {
             double c = cnt[b];
             if (c > 0.0) { double mx = sx[b] / c, my = sy[b] / c; sx[k] = mx; sy[k] = my; ++k; }
         }
-        double c4[4];
-        ok = (k > 0 && m_polyfit3(sx, sy, k, c4)) ? 1 : 0;
-        if (ok) { coef[0] = c4[0]; coef[1] = c4[1]; coef[2] = c4[2]; coef[3] = c4[3]; }
     }
-    ok = __shfl_sync(FULL, ok, 0);
+    k = __shfl_sync(FULL, k, 0);
+    __syncwarp();
+    int ok = 0;
+    if (k >= 4) ok = warp_polyfit3(sx, sy, k, coef, lane) ? 1 : 0;
+    else {
+        if (lane == 0) {
+            double c4[4];
+            ok = (k > 0 && m_polyfit3(sx, sy, k, c4)) ? 1 : 0;
+            if (ok) { coef[0] = c4[0]; coef[1] = c4[1]; coef[2] = c4[2]; coef[3] = c4[3]; }
+        }
+        ok = __shfl_sync(FULL, ok, 0);
+    }
     __syncwarp();
     return ok != 0;
 }
@@ -169,8 +233,8 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
 
         bool uniq_done = false; Uniq U;
         // change_quantiles cache
-        double cq_ql = -1.0, cq_qh = -1.0; int cq_abs = -1;
-        double cq_lo = 0.0, cq_hi = 0.0, cq_mean = 0.0; int cq_cnt = 0;
+        double cq_ql = -1.0, cq_qh = -1.0;
+        double cq_mean0 = 0.0, cq_mean1 = 0.0, cq_var0 = 0.0, cq_var1 = 0.0; int cq_cnt = 0;
         // friedrich cache
         int fr_r = -1; bool fr_ok = false;
         double* coef = scr + (A.nscr - 8);
@@ -219,40 +283,36 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
                 case TSFX_CHANGE_QUANTILES: {
                     if (d.p0 >= d.p1) { r = 0.0; break; }
                     if (!(d.p0 == cq_ql && d.p1 == cq_qh)) {
-                        cq_ql = d.p0; cq_qh = d.p1; cq_abs = -1;
-                        cq_lo = m_quantile_sorted(srt, n, d.p0);
-                        cq_hi = m_quantile_sorted(srt, n, d.p1);
-                    }
-                    if (cq_abs != d.i0) {
-                        cq_abs = d.i0;
+                        // one corridor = two passes that serve all four (isabs, f_agg) columns:
+                        // pass 1: count, sum d, sum |d| ; pass 2: centred squares of d and of |d|
+                        cq_ql = d.p0; cq_qh = d.p1;
+                        const double lo = m_quantile_sorted(srt, n, d.p0), hi = m_quantile_sorted(srt, n, d.p1);
                         int c = 0;
-                        double sm = 0.0;
+                        double s1 = 0.0, s1a = 0.0;
                         for (int i = lane; i + 1 < n; i += 32) {
-                            double a = (double)xs[i], b = (double)xs[i + 1];
-                            if (a >= cq_lo && a <= cq_hi && b >= cq_lo && b <= cq_hi) {
-                                double dx = b - a;
-                                if (cq_abs) dx = fabs(dx);
-                                sm += dx;
-                                ++c;
-                            }
+                            const double a = (double)xs[i], b = (double)xs[i + 1];
+                            if (a >= lo && a <= hi && b >= lo && b <= hi) { const double dx = b - a; s1 += dx; s1a += fabs(dx); ++c; }
                         }
                         cq_cnt = wsumi(c);
-                        cq_mean = wsum(sm) / (double)cq_cnt;
+                        cq_mean0 = wsum(s1) / (double)cq_cnt;
+                        cq_mean1 = wsum(s1a) / (double)cq_cnt;
+                        double q2 = 0.0, q2a = 0.0;
+                        if (cq_cnt > 0)
+                            for (int i = lane; i + 1 < n; i += 32) {
+                                const double a = (double)xs[i], b = (double)xs[i + 1];
+                                if (a >= lo && a <= hi && b >= lo && b <= hi) {
+                                    const double dx = b - a, e = dx - cq_mean0, ea = fabs(dx) - cq_mean1;
+                                    q2 = fma(e, e, q2);
+                                    q2a = fma(ea, ea, q2a);
+                                }
+                            }
+                        cq_var0 = wsum(q2) / (double)cq_cnt;
+                        cq_var1 = wsum(q2a) / (double)cq_cnt;
                     }
                     if (cq_cnt == 0) { r = 0.0; break; }
-                    if (d.attr == TSFX_AGG_MEAN) { r = cq_mean; break; }
-                    double q2 = 0.0;
-                    for (int i = lane; i + 1 < n; i += 32) {
-                        double a = (double)xs[i], b = (double)xs[i + 1];
-                        if (a >= cq_lo && a <= cq_hi && b >= cq_lo && b <= cq_hi) {
-                            double dx = b - a;
-                            if (cq_abs) dx = fabs(dx);
-                            dx -= cq_mean;
-                            q2 = fma(dx, dx, q2);
-                        }
-                    }
-                    double v = wsum(q2) / (double)cq_cnt;
-                    r = (d.attr == TSFX_AGG_STD) ? sqrt(v) : v;
+                    const double mu = d.i0 ? cq_mean1 : cq_mean0, va = d.i0 ? cq_var1 : cq_var0;
+                    if (d.attr == TSFX_AGG_MEAN) r = mu;
+                    else r = (d.attr == TSFX_AGG_STD) ? sqrt(va) : va;
                     break;
                 }
                 case TSFX_FRIEDRICH_COEFFICIENTS:

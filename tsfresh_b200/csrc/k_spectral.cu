@@ -141,9 +141,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
     // (no lock-step barrier here: measured slower -- the FFT stages dominate and are the same code for every warp)
-    for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
-        const bool live = (s0 + warp) < A.R.n_series;
-        const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
         const int n = load_series(A.R, s, xs, lane);
         double* orow = A.out + (size_t)s * A.ncols;
 
@@ -207,22 +205,26 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
             am0 = wsum(am0); am1 = wsum(am1); am2 = wsum(am2); am3 = wsum(am3); am4 = wsum(am4);
         }
 
-        for (int j = 0; j < A.nd; ++j) {
+        // fft_coefficient columns are O(1) reads of the spectrum: evaluated LANE-PARALLEL (the descriptors are
+        // the first A.nfft of the group, ordered by attr so a round of 32 lanes mostly shares one branch)
+        for (int j = lane; j < A.nfft; j += 32) {
+            const Desc d = A.descs[j];
+            double r = dnan();
+            if (d.i0 < nb) {
+                const double2 z = X[d.i0];
+                switch (d.attr) {
+                    case TSFX_FFT_REAL: r = z.x; break;
+                    case TSFX_FFT_IMAG: r = z.y; break;
+                    case TSFX_FFT_ABS: r = hypot(z.x, z.y); break;
+                    default: r = atan2(z.y, z.x) * (180.0 / 3.14159265358979323846); break;
+                }
+            }
+            orow[d.col] = r;
+        }
+        for (int j = A.nfft; j < A.nd; ++j) {
             const Desc d = A.descs[j];
             double r = dnan();
             switch (d.calc) {
-                case TSFX_FFT_COEFFICIENT: {
-                    if (d.i0 < nb) {
-                        double2 z = X[d.i0];
-                        switch (d.attr) {
-                            case TSFX_FFT_REAL: r = z.x; break;
-                            case TSFX_FFT_IMAG: r = z.y; break;
-                            case TSFX_FFT_ABS: r = hypot(z.x, z.y); break;
-                            default: r = atan2(z.y, z.x) * (180.0 / 3.14159265358979323846); break;
-                        }
-                    }
-                    break;
-                }
                 case TSFX_FFT_AGGREGATED: {
                     double m1 = am1 / am0, m2 = am2 / am0, m3 = am3 / am0, m4 = am4 / am0;
                     double var = m2 - m1 * m1;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
                 }
                 default: break;
             }
-            if (lane == 0 && live) orow[d.col] = r;
+            if (lane == 0) orow[d.col] = r;
         }
         __syncwarp();
     }

@@ -58,6 +58,7 @@ struct tsfx_plan {
     Desc* dev[G_COUNT] = {nullptr};
     int32_t* d_final_col = nullptr;   // final column of every staged column, groups concatenated
     int basic_nfin = 0;               // leading "finisher" descriptors of the BASIC group
+    int spectral_nfft = 0;            // leading fft_coefficient descriptors of the SPECTRAL group
     int cum[G_COUNT + 1] = {0};
     int ncols = 0;
     int lag_needed = 0, pacf_want = -1;
@@ -253,6 +254,11 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
                 const bool fa = basic_finisher_calc(a.calc), fb = basic_finisher_calc(b.calc);
                 if (fa != fb) return fa;
             }
+            if (g == G_SPECTRAL) {            // fft_coefficient first, grouped by attribute
+                const bool fa = a.calc == TSFX_FFT_COEFFICIENT, fb = b.calc == TSFX_FFT_COEFFICIENT;
+                if (fa != fb) return fa;
+                if (fa && a.attr != b.attr) return a.attr < b.attr;
+            }
             if (a.calc != b.calc) return a.calc < b.calc;
             if (a.i1 != b.i1) return a.i1 < b.i1;
             if (a.i2 != b.i2) return a.i2 < b.i2;
@@ -263,6 +269,8 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
         });
         if (g == G_BASIC)
             for (const Desc& d : P->host[g]) P->basic_nfin += basic_finisher_calc(d.calc) ? 1 : 0;
+        if (g == G_SPECTRAL)
+            for (const Desc& d : P->host[g]) P->spectral_nfft += (d.calc == TSFX_FFT_COEFFICIENT) ? 1 : 0;
         P->cum[g + 1] = P->cum[g] + (int)P->host[g].size();
         for (size_t j = 0; j < P->host[g].size(); ++j) {      // col becomes the index inside the group's staging row
             final_col.push_back(P->host[g][j].col);
@@ -376,6 +384,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 A.tables = P->d_tables; A.table_off = P->d_toff; A.table_half = P->d_thalf;
                 A.need_fft = P->need_fft; A.need_welch = P->need_welch;
                 A.max_hist = P->fourier_bins;
+                A.nfft = P->spectral_nfft;
                 e = launch_spectral(A, max_len, ctx->stream, ctx->sm_count);
                 break;
             }

@@ -64,6 +64,7 @@ struct SpectralArgs {
     const int32_t* table_half;
     int need_fft, need_welch;
     int max_hist;
+    int nfft;                  // the first nfft descriptors are fft_coefficient (lane-parallel stage)
 };
 cudaError_t launch_spectral(const SpectralArgs& A, int max_len, cudaStream_t st, int sm_count);
 
