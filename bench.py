@@ -272,8 +272,12 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    if world == 1:
-        group_ms = ctx.timings()          # CUDA events recorded around each kernel group of the LAST timed step
+    # per-group CUDA events: taken from the last timed step at N=1, from one extra (untimed) pass over this rank's
+    # shard at N>1 (the timed steps there are split into row blocks for the all-gather overlap)
+    if world > 1:
+        dp.extract_dense_device(values.data_ptr(), S, L, out.data_ptr(), timing=True)
+        torch.cuda.synchronize()
+    group_ms = ctx.timings()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -281,6 +285,8 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = world * S / (ms_step / 1e3)
     launches_per_step = ctx.launch_count() * (1 if world == 1 else n_blocks)
+    if rank != 0:
+        group_ms = {}
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
     e2e = None

@@ -216,13 +216,15 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             rows = np.searchsorted(all_ids, uid)
             data[rows, c0:c0 + len(names)] = mat
             c0 += len(names)
-    result = pd.DataFrame(data, index=pd.Index(index), columns=columns, dtype=float)
+    # the float64 matrix the device wrote becomes the frame's block as is (no copy)
+    result = pd.DataFrame(np.asarray(data, dtype=np.float64), index=pd.Index(index), columns=columns, copy=False)
     if id_dtype is not None:
         try:
             result.index = result.index.astype(id_dtype)
         except (TypeError, ValueError):
             pass
-    result = result.sort_index()
+    if not result.index.is_monotonic_increasing:
+        result = result.sort_index()
     if impute_function is not None:
         impute_function(result)
     return result
