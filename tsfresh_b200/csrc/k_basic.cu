@@ -333,7 +333,7 @@ __device__ __noinline__ double basic_finisher(const Desc& d, const double* ST, c
 }
 
 template <int WPC>
-__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 2 : 1)) k_basic(BasicArgs A) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;

@@ -20,6 +20,10 @@ __device__ __forceinline__ void count_le(int& c, double m, double tau) {
 }
 // max of two non-NaN magnitudes without fmax()'s NaN handling (DSETP + SEL instead of DSETP.MAX/FSEL/SEL/LOP3)
 __device__ __forceinline__ double max_nn(double a, double b) { return a > b ? a : b; }
+// |x| as one integer AND on the high word (keeps the half-rate FP64 pipe for the subtractions and compares)
+__device__ __forceinline__ double abs_bits(double x) {
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
 
 template <int NT>
 __device__ __forceinline__ void entropy_sweep(const double* xd, int n, const double (&tau)[NT], double (&sum_ln2)[NT],
@@ -39,14 +43,14 @@ __device__ __forceinline__ void entropy_sweep(const double* xd, int n, const dou
         double b0 = xd[0], b1 = xd[1];
         for (int j = 0; j < n3; ++j) {
             const double b2 = xd[j + 2];
-            const double m2 = max_nn(fabs(a0 - b0), fabs(a1 - b1));
-            const double m3 = max_nn(m2, fabs(a2 - b2));
+            const double m2 = max_nn(abs_bits(a0 - b0), abs_bits(a1 - b1));
+            const double m3 = max_nn(m2, abs_bits(a2 - b2));
 #pragma unroll
             for (int t = 0; t < NT; ++t) { count_le(c2[t], m2, tau[t]); count_le(c3[t], m3, tau[t]); }
             b0 = b1; b1 = b2;
         }
         {   // last length-2 template j = n2 - 1
-            const double m2 = max_nn(fabs(a0 - b0), fabs(a1 - b1));
+            const double m2 = max_nn(abs_bits(a0 - b0), abs_bits(a1 - b1));
 #pragma unroll
             for (int t = 0; t < NT; ++t) count_le(c2[t], m2, tau[t]);
         }
