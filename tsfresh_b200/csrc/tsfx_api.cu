@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,6 +15,20 @@
 using namespace tsfx;
 
 static std::string g_create_error;
+
+namespace tsfx {
+int grid_waves(int dflt) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TSFX_GRID_WAVES"); v = e ? atoi(e) : 0; }
+    return v > 0 ? v : dflt;
+}
+}  // namespace tsfx
+
+static int env_streams() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TSFX_STREAMS"); v = e ? atoi(e) : 1; if (v < 1) v = 1; if (v > 4) v = 4; }
+    return v;
+}
 
 struct DevBuf {
     void* p = nullptr;
@@ -49,6 +64,8 @@ struct tsfx_ctx {
     CsrWorkspace csr;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host path
+    cudaStream_t s_side[3] = {nullptr, nullptr, nullptr};   // optional side streams so kernel groups can overlap
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
@@ -147,6 +164,8 @@ extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
     for (int g = 0; g < G_EVENTS; ++g) { CKC(cudaEventCreate(&ctx->ev[g][0])); CKC(cudaEventCreate(&ctx->ev[g][1])); }
     CKC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) { CKC(cudaStreamCreateWithFlags(&ctx->s_side[i], cudaStreamNonBlocking)); CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     for (int i = 0; i < 2; ++i) { CKC(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
     // decimal threshold table d * 10^k (correctly rounded literals via strtod)
     {
@@ -174,6 +193,8 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     if (ctx->d_dec) cudaFree(ctx->d_dec);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     for (int g = 0; g < G_EVENTS; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
+    for (int i = 0; i < 3; ++i) { if (ctx->s_side[i]) cudaStreamDestroy(ctx->s_side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
@@ -339,6 +360,21 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
     CK(ctx->stage.reserve((size_t)R.n_series * staged * sizeof(double)));
     double* const d_final = d_out;
     (void)d_final;
+    if (!P->host[G_SPECTRAL].empty()) {      // FFT twiddle table (filled once, on the main stream, before any fork)
+        int p2 = 1;
+        while (p2 < max_len) p2 <<= 1;
+        if (p2 > max_len) p2 >>= 1;            // largest power of two <= max_len
+        p2 = std::max(p2, 256);
+        int rc = ensure_twiddle(ctx, p2);
+        if (rc) return rc;
+    }
+    // kernel groups are independent (own staging matrix): optionally spread them over side streams
+    const int nstreams = timing ? 1 : env_streams();
+    if (nstreams > 1) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int i = 0; i < nstreams - 1; ++i) CK(cudaStreamWaitEvent(ctx->s_side[i], ctx->ev_fork, 0));
+    }
+    int launched = 0;
     if (max_len < 1) return fail(ctx, TSFX_E_INVALID, "series of length < 1");
     auto too_long = [&](const char* g) {
         return fail(ctx, TSFX_E_TOO_LONG, std::string("series length ") + std::to_string(max_len) +
@@ -349,6 +385,8 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         if (timing) { CK(cudaEventRecord(ctx->ev[g][0], ctx->stream)); }
         cudaError_t e = cudaSuccess;
         double* d_out = (double*)ctx->stage.p + (size_t)R.n_series * P->cum[g];      // this group's staging matrix
+        const int sidx = launched++ % nstreams;
+        cudaStream_t gs = (sidx == 0) ? ctx->stream : ctx->s_side[sidx - 1];
         const int g_ncols = (int)P->host[g].size();
         switch (g) {
             case G_BASIC: {
@@ -361,44 +399,38 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 A.nlag = even(P->lag_needed + 1 + pac);
                 A.nscr = even(std::max(std::max(max_len, 64), (P->basic_bins + 1) / 2));
                 A.dec = ctx->d_dec;
-                e = launch_basic(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_basic(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SORTED: {
                 SortedArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = even(4 * (P->friedrich_r + 2) + 16);
-                e = launch_sorted(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_sorted(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SPECTRAL: {
                 SpectralArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
-                int p2 = 1;
-                while (p2 < max_len) p2 <<= 1;
-                if (p2 > max_len) p2 >>= 1;            // largest power of two <= max_len
-                p2 = std::max(p2, 256);
-                int rc = ensure_twiddle(ctx, p2);
-                if (rc) return rc;
                 A.twiddle = ctx->d_tw; A.tw_n = ctx->tw_n;
                 A.tables = P->d_tables; A.table_off = P->d_toff; A.table_half = P->d_thalf;
                 A.need_fft = P->need_fft; A.need_welch = P->need_welch;
                 A.max_hist = P->fourier_bins;
                 A.nfft = P->spectral_nfft;
-                e = launch_spectral(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_spectral(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_LA: {
                 LaArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = P->max_ar_k;
-                e = launch_la(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_la(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_ENTROPY: {
                 EntropyArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
-                e = launch_entropy(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_entropy(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SEQ: {
@@ -406,14 +438,14 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
                          (std::min(P->n_lz, 255) << 16);
-                e = launch_seq(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_seq(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_PEAKS: {
                 SeqArgs A;
                 A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_cwt_peaks_n << 8);
-                e = launch_peaks(A, max_len, ctx->stream, ctx->sm_count);
+                e = launch_peaks(A, max_len, gs, ctx->sm_count);
                 break;
             }
         }
@@ -422,6 +454,11 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         ctx->launches += 1;
         if (timing) { CK(cudaEventRecord(ctx->ev[g][1], ctx->stream)); ctx->ev_used[g] = true; }
     }
+    if (nstreams > 1)
+        for (int i = 0; i < nstreams - 1; ++i) {
+            CK(cudaEventRecord(ctx->ev_join[i], ctx->s_side[i]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+        }
     {   // scatter the staging matrices into the caller's [n_series x ncols] matrix
         if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][0], ctx->stream)); }
         AssembleArgs A;

@@ -8,6 +8,10 @@
 
 namespace tsfx {
 
+// CTAs per SM in a launch (each CTA loops over its share of the series).  TSFX_GRID_WAVES overrides the
+// per-kernel default (tuning knob, read once).
+int grid_waves(int dflt);
+
 enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_PEAKS, G_COUNT };
 #define G_EVENTS (G_COUNT + 1)      // + the assemble pass
 
