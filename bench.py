@@ -256,6 +256,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    multi_stream = int(os.environ.get("TSFX_STREAMS", "1")) > 1      # groups overlap: per-group events need a separate pass
     for _ in range(args.warmup):
         step()
     barrier()
@@ -266,15 +267,13 @@ def main():
     group_ms = {}
     e0.record(stream)
     for _ in range(args.steps):
-        step(timing=(world == 1))
-        if world == 1:
-            pass
+        step(timing=(world == 1 and not multi_stream))
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     # per-group CUDA events: taken from the last timed step at N=1, from one extra (untimed) pass over this rank's
     # shard at N>1 (the timed steps there are split into row blocks for the all-gather overlap)
-    if world > 1:
+    if world > 1 or multi_stream:
         dp.extract_dense_device(values.data_ptr(), S, L, out.data_ptr(), timing=True)
         torch.cuda.synchronize()
     group_ms = ctx.timings()

@@ -672,7 +672,7 @@ cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int 
     if (per * wpc > 227 * 1024) return cudaErrorInvalidConfiguration;
     size_t smem = per * wpc;
     int64_t ctas = (A.R.n_series + wpc - 1) / wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(16);
+    int64_t cap = (int64_t)sm_count * grid_waves(4096);
     int grid = (int)(ctas < cap ? ctas : cap);
     if (grid < 1) grid = 1;
 #define TSFX_LAUNCH_BASIC(W)                                                                              \

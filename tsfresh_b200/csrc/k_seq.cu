@@ -484,7 +484,7 @@ static void seq_geometry(size_t per, int sm_count, int64_t n_series, int* wpc_ou
     wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
     *wpc_out = wpc;
     *smem_out = per * wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(16);
+    int64_t cap = (int64_t)sm_count * grid_waves(4096);
     *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_series + wpc - 1) / wpc, cap));
 }
 

@@ -302,7 +302,7 @@ cudaError_t launch_spectral(const SpectralArgs& A0, int max_len, cudaStream_t st
     int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 100 * 1024 / per));
     wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
     size_t smem = per * wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(16);
+    int64_t cap = (int64_t)sm_count * grid_waves(4096);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
 #define TSFX_LAUNCH(W)                                                                                       \
     {                                                                                                        \
