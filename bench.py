@@ -329,9 +329,21 @@ def main():
                 groups[g] = {"ms": ms, "columns": ncols.get(g, 0), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
             dom = max(group_ms, key=lambda g: group_ms[g])
             ach = groups[dom]["algorithmic_GBps"]
+            traffic, limiter = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+                w = tj["workload"]
+                if (w["series"], w["len"], w["settings"]) == (S, L, args.settings) and ("k_" + dom) in tj:
+                    traffic = tj["k_" + dom]["traffic_bytes"] / 1e9
+                    limiter = "ncu: fp64 pipe %.0f%% active, issue %.0f%% active" % (
+                        tj["k_" + dom]["fp64_pipe_active_pct"], tj["k_" + dom]["issue_active_pct"])
+            except Exception:
+                pass
             roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                         "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650 GB/s",
-                        "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                        "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                        "algorithmic_GB_per_launch": S * (4 * L + 8 * ncols.get(dom, 0)) / 1e9,
+                        "limiter": limiter or "the dominant kernel is FP64-issue bound, not HBM bound (DESIGN.md section 4)",
                         "whole_pass_GBps": S * (4 * L + 12 + 8 * F) / (ms_step * 1e-3) / 1e9,
                         "groups": groups}
         cb = None
