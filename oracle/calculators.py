@@ -295,16 +295,16 @@ def _friedrich_fit(x, m, r):  # :131-173
 
 @combiner
 def friedrich_coefficients(x, param):  # :2082-2130
-    cache, out = {}, []
+    cache, res = {}, {}
     for p in param:
         key = (p["m"], p["r"])
         if key not in cache:
             cache[key] = _friedrich_fit(x, p["m"], p["r"])
         try:
-            out.append(cache[key][p["coeff"]])
+            res[(p["coeff"], p["m"], p["r"])] = cache[key][p["coeff"]]
         except IndexError:
-            out.append(NAN)
-    return out
+            res[(p["coeff"], p["m"], p["r"])] = NAN
+    return list(res.values())          # dict result: duplicate keys collapse (:2126-2130)
 
 
 @simple
@@ -387,7 +387,7 @@ def ar_coefficient(x, param):  # :1459-1507
                 res[(c, k)] = 0
         else:
             res[(c, k)] = NAN
-    return [res[(p["coeff"], p["k"])] for p in param]
+    return list(res.values())          # the reference returns list(res.items()): duplicate keys collapse
 
 
 @simple
