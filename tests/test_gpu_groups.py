@@ -113,3 +113,23 @@ def test_efficient(ctx):
     bad, plan, got, want = gpu_vs_oracle(ctx, EfficientFCParameters(), series)
     assert plan.n_cols == 777
     assert not bad, _report(bad)
+
+
+@pytest.mark.parametrize("length,count", [(1300, 4), (3000, 3)])
+def test_long_series_efficient(ctx, length, count):
+    """lengths beyond one 1024-sample tile (multi-tile run-length words, acf(fft=True) threshold n > 1250 in the
+    reference, direct-DFT path for non-power-of-two lengths, 7+ Welch segments)"""
+    series = list(synthetic_series(77, count, length, "walk")) + list(synthetic_series(78, 2, length, "normal"))
+    bad, *_ = gpu_vs_oracle(ctx, EfficientFCParameters(), series)
+    assert not bad, _report(bad)
+
+
+def test_series_too_long_is_an_error_not_garbage(ctx):
+    from tests.helpers import to_csr
+    from tsfresh_b200._lib import DevicePlan
+    from tsfresh_b200.plan import Plan
+    dp = DevicePlan(ctx, Plan(ComprehensiveFCParameters()))
+    values, begin, lens = to_csr([np.zeros(60000, np.float32)])
+    with pytest.raises(ValueError, match="exceeds the shared-memory staging"):
+        dp.extract_csr(values, begin, lens)
+    dp.close()
