@@ -336,7 +336,7 @@ template <int WPC>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xc = reinterpret_cast<double*>(base);
     double* scr = xc + A.npad;
     double* lagS = scr + A.nscr;
@@ -666,28 +666,10 @@ cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int 
     size_t per = (size_t)A.npad * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + 32 * 8 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
-    int wpc = (int)(100 * 1024 / per);
-    if (wpc < 1) wpc = 1;
-    if (wpc > 8) wpc = 8;
-    if (per * wpc > 227 * 1024) return cudaErrorInvalidConfiguration;
-    size_t smem = per * wpc;
-    int64_t ctas = (A.R.n_series + wpc - 1) / wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(4096);
-    int grid = (int)(ctas < cap ? ctas : cap);
-    if (grid < 1) grid = 1;
-#define TSFX_LAUNCH_BASIC(W)                                                                              \
-    {                                                                                                     \
-        cudaError_t e = cudaFuncSetAttribute(k_basic<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                   \
-        k_basic<W><<<grid, W * 32, smem, st>>>(A);                                                        \
-    }
-    switch (wpc) {
-        case 8: TSFX_LAUNCH_BASIC(8) break;
-        case 7: case 6: case 5: case 4: wpc = 4; smem = per * 4; grid = (int)std::min<int64_t>((A.R.n_series + 3) / 4, cap); TSFX_LAUNCH_BASIC(4) break;
-        case 3: case 2: wpc = 2; smem = per * 2; grid = (int)std::min<int64_t>((A.R.n_series + 1) / 2, cap); TSFX_LAUNCH_BASIC(2) break;
-        default: wpc = 1; smem = per; grid = (int)std::min<int64_t>(A.R.n_series, cap); TSFX_LAUNCH_BASIC(1) break;
-    }
-#undef TSFX_LAUNCH_BASIC
+    Geometry G;
+    if (!plan_geometry(per, 100 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
+    A.gscratch = G.gscratch;
+    TSFX_DISPATCH(k_basic, G, st, A)
     return cudaGetLastError();
 }
 

@@ -98,7 +98,7 @@ template <int WPC>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 3 : 1)) k_entropy(EntropyArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xd = reinterpret_cast<double*>(base);
     float* xs = reinterpret_cast<float*>(xd + A.npad + 2);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
@@ -128,25 +128,10 @@ cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, 
     size_t per = (size_t)(A.npad + 2) * 8 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
-    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
-    int wpc = (int)std::min<size_t>(4, std::max<size_t>(1, 64 * 1024 / per));
-    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
-    size_t smem = per * wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(4096);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((A.R.n_series + wpc - 1) / wpc, cap));
-#define TSFX_LAUNCH(W)                                                                                      \
-    {                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(k_entropy<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                     \
-        k_entropy<W><<<grid, W * 32, smem, st>>>(A);                                                        \
-    }
-    switch (wpc) {
-        case 8: TSFX_LAUNCH(8) break;
-        case 4: TSFX_LAUNCH(4) break;
-        case 2: TSFX_LAUNCH(2) break;
-        default: TSFX_LAUNCH(1) break;
-    }
-#undef TSFX_LAUNCH
+    Geometry G;
+    if (!plan_geometry(per, 64 * 1024, 4, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
+    A.gscratch = G.gscratch;
+    TSFX_DISPATCH(k_entropy, G, st, A)
     return cudaGetLastError();
 }
 

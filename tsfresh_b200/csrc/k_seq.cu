@@ -149,7 +149,7 @@ template <int WPC>
 __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
     unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
@@ -302,7 +302,7 @@ template <int WPC>
 __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * A.bytes_per_warp;
+    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* row0 = reinterpret_cast<double*>(base);                       // npad : width-1 row (float64)
     double* tmp = row0 + Y.npad;                                           // npad : the row being formed
     double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad : memoised noise floor (NaN = not yet)
@@ -479,22 +479,6 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     }
 }
 
-static void seq_geometry(size_t per, int sm_count, int64_t n_series, int* wpc_out, size_t* smem_out, int* grid_out) {
-    int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, 72 * 1024 / per));
-    wpc = wpc >= 8 ? 8 : wpc >= 4 ? 4 : wpc >= 2 ? 2 : 1;
-    *wpc_out = wpc;
-    *smem_out = per * wpc;
-    int64_t cap = (int64_t)sm_count * grid_waves(4096);
-    *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_series + wpc - 1) / wpc, cap));
-}
-
-#define TSFX_LAUNCH_K(KERNEL, W)                                                                        \
-    {                                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(KERNEL<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                 \
-        KERNEL<W><<<grid, W * 32, smem, st>>>(A, Y);                                                    \
-    }
-
 // lempel_ziv_complexity + permutation_entropy
 cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     SeqArgs A = A0;
@@ -519,16 +503,10 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
     size_t per = (off + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
-    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
-    int wpc, grid;
-    size_t smem;
-    seq_geometry(per, sm_count, A.R.n_series, &wpc, &smem, &grid);
-    switch (wpc) {
-        case 8: TSFX_LAUNCH_K(k_seq, 8) break;
-        case 4: TSFX_LAUNCH_K(k_seq, 4) break;
-        case 2: TSFX_LAUNCH_K(k_seq, 2) break;
-        default: TSFX_LAUNCH_K(k_seq, 1) break;
-    }
+    Geometry G;
+    if (!plan_geometry(per, 72 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
+    A.gscratch = G.gscratch;
+    TSFX_DISPATCH(k_seq, G, st, A, Y)
     return cudaGetLastError();
 }
 
@@ -536,7 +514,7 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
 cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     SeqArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    if (max_len > 32000) return cudaErrorInvalidConfiguration;
+    if (max_len > 32000) return cudaErrorInvalidConfiguration;      // int16 line tables
     SeqLayout Y = {};
     Y.npad = A.npad;
     Y.nwords = (A.npad + 31) / 32 + 1;
@@ -554,16 +532,10 @@ cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
     size_t per = (off + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
-    if (per > 227 * 1024) return cudaErrorInvalidConfiguration;
-    int wpc, grid;
-    size_t smem;
-    seq_geometry(per, sm_count, A.R.n_series, &wpc, &smem, &grid);
-    switch (wpc) {
-        case 8: TSFX_LAUNCH_K(k_peaks, 8) break;
-        case 4: TSFX_LAUNCH_K(k_peaks, 4) break;
-        case 2: TSFX_LAUNCH_K(k_peaks, 2) break;
-        default: TSFX_LAUNCH_K(k_peaks, 1) break;
-    }
+    Geometry G;
+    if (!plan_geometry(per, 72 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
+    A.gscratch = G.gscratch;
+    TSFX_DISPATCH(k_peaks, G, st, A, Y)
     return cudaGetLastError();
 }
 

@@ -358,6 +358,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
     const int staged = P->cum[G_COUNT];
     if (staged == 0) return TSFX_OK;
     CK(ctx->stage.reserve((size_t)R.n_series * staged * sizeof(double)));
+    if (max_len > 1024) CK(ctx->misc.reserve((size_t)1 << 30));      // global working regions for series too long for shared memory
     double* const d_final = d_out;
     (void)d_final;
     if (!P->host[G_SPECTRAL].empty()) {      // FFT twiddle table (filled once, on the main stream, before any fork)
@@ -391,7 +392,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         switch (g) {
             case G_BASIC: {
                 BasicArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.lag_needed = P->lag_needed;
                 A.nfin = P->basic_nfin;
                 int pac = P->pacf_want >= 0 ? 4 * (P->pacf_want + 1) : 0;
@@ -404,14 +405,14 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_SORTED: {
                 SortedArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = even(4 * (P->friedrich_r + 2) + 16);
                 e = launch_sorted(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SPECTRAL: {
                 SpectralArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.twiddle = ctx->d_tw; A.tw_n = ctx->tw_n;
                 A.tables = P->d_tables; A.table_off = P->d_toff; A.table_half = P->d_thalf;
                 A.need_fft = P->need_fft; A.need_welch = P->need_welch;
@@ -422,20 +423,20 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_LA: {
                 LaArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = P->max_ar_k;
                 e = launch_la(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_ENTROPY: {
                 EntropyArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 e = launch_entropy(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SEQ: {
                 SeqArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
                          (std::min(P->n_lz, 255) << 16);
                 e = launch_seq(A, max_len, gs, ctx->sm_count);
@@ -443,7 +444,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_PEAKS: {
                 SeqArgs A;
-                A.R = R; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_cwt_peaks_n << 8);
                 e = launch_peaks(A, max_len, gs, ctx->sm_count);
                 break;

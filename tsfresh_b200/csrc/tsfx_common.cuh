@@ -62,6 +62,15 @@ __device__ __forceinline__ int wmini(int v) { return __reduce_min_sync(FULL, v);
 // count of lanes (x tiles) where pred holds; every lane must call with its own predicate
 __device__ __forceinline__ int wcount(bool pred) { return __popc(__ballot_sync(FULL, pred)); }
 
+// ---------------------------------------------------------------- per-warp working region
+// Normally a slice of the CTA's dynamic shared memory.  Series too long for that (bytes_per_warp > 227 KB) run
+// with the same carve-up in a global-memory scratch buffer (L2-resident; slower, but every length works).
+__device__ __forceinline__ unsigned char* warp_region(unsigned char* smem_raw, unsigned char* gscratch, int bytes_per_warp,
+                                                      int wpc, int warp) {
+    return gscratch ? gscratch + ((size_t)blockIdx.x * wpc + warp) * (size_t)bytes_per_warp
+                    : smem_raw + (size_t)warp * bytes_per_warp;
+}
+
 // ---------------------------------------------------------------- series staging
 // Loads series s into shared memory xs[0..n) (coalesced; 128-bit loads when the start is 16B aligned).
 __device__ __forceinline__ int load_series(const SeriesRef& R, int64_t s, float* xs, int lane) {

@@ -12,6 +12,55 @@ namespace tsfx {
 // per-kernel default (tuning knob, read once).
 int grid_waves(int dflt);
 
+struct Geometry { int wpc; size_t smem; int grid; unsigned char* gscratch; };
+
+// Chooses warps per CTA / grid for a warp-per-series kernel needing `per` bytes per warp.  Shared memory when it
+// fits (budget = target bytes per CTA so several CTAs stay resident), else the global scratch buffer.
+inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series, int sm_count, unsigned char* gs,
+                          size_t gs_bytes, Geometry* G) {
+    if (per <= 227 * 1024) {
+        size_t w = budget / per;
+        int wpc = w >= 8 ? 8 : w >= 4 ? 4 : w >= 2 ? 2 : 1;
+        while (wpc > maxw) wpc >>= 1;
+        G->wpc = wpc;
+        G->smem = per * wpc;
+        int64_t cap = (int64_t)sm_count * grid_waves(4096);
+        int64_t ctas = (n_series + wpc - 1) / wpc;
+        G->grid = (int)(ctas < cap ? (ctas < 1 ? 1 : ctas) : cap);
+        G->gscratch = nullptr;
+        return true;
+    }
+    int wpc = 4;
+    if (wpc > maxw) wpc = maxw;
+    size_t max_ctas = gs ? gs_bytes / (per * wpc) : 0;
+    if (max_ctas < 1) { wpc = 1; max_ctas = gs ? gs_bytes / per : 0; }
+    if (max_ctas < 1) return false;
+    int64_t ctas = (n_series + wpc - 1) / wpc;
+    int64_t cap = (int64_t)sm_count * 4;
+    if ((int64_t)max_ctas < cap) cap = (int64_t)max_ctas;
+    G->wpc = wpc;
+    G->smem = 0;
+    G->grid = (int)(ctas < cap ? (ctas < 1 ? 1 : ctas) : cap);
+    G->gscratch = gs;
+    return true;
+}
+
+#define TSFX_LAUNCH_GEOM(KERNEL, W, G, st, ...)                                                                   \
+    {                                                                                                             \
+        if ((G).smem) {                                                                                           \
+            cudaError_t e__ = cudaFuncSetAttribute(KERNEL<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G).smem); \
+            if (e__ != cudaSuccess) return e__;                                                                   \
+        }                                                                                                         \
+        KERNEL<W><<<(G).grid, W * 32, (G).smem, st>>>(__VA_ARGS__);                                               \
+    }
+#define TSFX_DISPATCH(KERNEL, G, st, ...)                                          \
+    switch ((G).wpc) {                                                             \
+        case 8: TSFX_LAUNCH_GEOM(KERNEL, 8, G, st, __VA_ARGS__) break;             \
+        case 4: TSFX_LAUNCH_GEOM(KERNEL, 4, G, st, __VA_ARGS__) break;             \
+        case 2: TSFX_LAUNCH_GEOM(KERNEL, 2, G, st, __VA_ARGS__) break;             \
+        default: TSFX_LAUNCH_GEOM(KERNEL, 1, G, st, __VA_ARGS__) break;            \
+    }
+
 enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_PEAKS, G_COUNT };
 #define G_EVENTS (G_COUNT + 1)      // + the assemble pass
 
@@ -31,6 +80,8 @@ cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count
 
 struct BasicArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;   // device, this group's descriptors
     int nd;
     double* out;
@@ -46,6 +97,8 @@ bool basic_finisher_calc(int calc);     // host: is this calculator evaluated by
 
 struct SortedArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;
     int nd;
     double* out;
@@ -56,6 +109,8 @@ cudaError_t launch_sorted(const SortedArgs& A, int max_len, cudaStream_t st, int
 
 struct SpectralArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;
     int nd;
     double* out;
@@ -74,6 +129,8 @@ cudaError_t launch_spectral(const SpectralArgs& A, int max_len, cudaStream_t st,
 
 struct LaArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;
     int nd;
     double* out;
@@ -84,6 +141,8 @@ cudaError_t launch_la(const LaArgs& A, int max_len, cudaStream_t st, int sm_coun
 
 struct EntropyArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;
     int nd;
     double* out;
@@ -94,6 +153,8 @@ cudaError_t launch_entropy(const EntropyArgs& A, int max_len, cudaStream_t st, i
 
 struct SeqArgs {
     SeriesRef R;
+    unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
+    size_t gscratch_bytes;
     const Desc* descs;
     int nd;
     double* out;
