@@ -332,11 +332,11 @@ __device__ __noinline__ double basic_finisher(const Desc& d, const double* ST, c
     }
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xc = reinterpret_cast<double*>(base);
     double* scr = xc + A.npad;
     double* lagS = scr + A.nscr;

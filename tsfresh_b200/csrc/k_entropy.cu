@@ -94,11 +94,11 @@ __device__ __forceinline__ void entropy_batch(const Desc* descs, int j0, int cnt
     }
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 3 : 1)) k_entropy(EntropyArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xd = reinterpret_cast<double*>(base);
     float* xs = reinterpret_cast<float*>(xd + A.npad + 2);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;

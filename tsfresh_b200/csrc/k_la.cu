@@ -91,11 +91,11 @@ __device__ __forceinline__ void warp_backward(const double* L, int q, int lda, d
     }
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xc = reinterpret_cast<double*>(base);          // npad : centred series (level)
     double* dx = xc + A.npad;                              // npad : first differences
     double* G = dx + A.npad;                               // pmax*pmax

@@ -145,11 +145,11 @@ __device__ __forceinline__ unsigned pe_lehmer(unsigned bits, int D) {
     return code;            // digit D-1 is always 0 (radix 1)
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
     unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
@@ -298,11 +298,11 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     }
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* row0 = reinterpret_cast<double*>(base);                       // npad : width-1 row (float64)
     double* tmp = row0 + Y.npad;                                           // npad : the row being formed
     double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad : memoised noise floor (NaN = not yet)

@@ -199,11 +199,11 @@ __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt,
     return ok != 0;
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* scr = reinterpret_cast<double*>(base);
     float* xs = reinterpret_cast<float*>(scr + A.nscr);
     float* srt = xs + A.npad;

@@ -128,11 +128,11 @@ __device__ __forceinline__ int hist_bin_s(double v, double first, double last, d
     return idx;
 }
 
-template <int WPC>
+template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab, int nhist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double2* X = reinterpret_cast<double2*>(base);                // nspec
     double2* wtab = X + A.nspec;                                  // nwtab
     double* pxx = reinterpret_cast<double*>(wtab + nwtab);        // 130

@@ -65,10 +65,12 @@ __device__ __forceinline__ int wcount(bool pred) { return __popc(__ballot_sync(F
 // ---------------------------------------------------------------- per-warp working region
 // Normally a slice of the CTA's dynamic shared memory.  Series too long for that (bytes_per_warp > 227 KB) run
 // with the same carve-up in a global-memory scratch buffer (L2-resident; slower, but every length works).
+// (compile-time switch: the shared-memory instantiation keeps pure shared-space addressing)
+template <bool GLOBAL_SCRATCH>
 __device__ __forceinline__ unsigned char* warp_region(unsigned char* smem_raw, unsigned char* gscratch, int bytes_per_warp,
                                                       int wpc, int warp) {
-    return gscratch ? gscratch + ((size_t)blockIdx.x * wpc + warp) * (size_t)bytes_per_warp
-                    : smem_raw + (size_t)warp * bytes_per_warp;
+    if (GLOBAL_SCRATCH) return gscratch + ((size_t)blockIdx.x * wpc + warp) * (size_t)bytes_per_warp;
+    return smem_raw + (size_t)warp * bytes_per_warp;
 }
 
 // ---------------------------------------------------------------- series staging

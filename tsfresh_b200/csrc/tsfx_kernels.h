@@ -30,8 +30,7 @@ inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series,
         G->gscratch = nullptr;
         return true;
     }
-    int wpc = 4;
-    if (wpc > maxw) wpc = maxw;
+    int wpc = maxw >= 4 ? 4 : 1;
     size_t max_ctas = gs ? gs_bytes / (per * wpc) : 0;
     if (max_ctas < 1) { wpc = 1; max_ctas = gs ? gs_bytes / per : 0; }
     if (max_ctas < 1) return false;
@@ -45,20 +44,24 @@ inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series,
     return true;
 }
 
-#define TSFX_LAUNCH_GEOM(KERNEL, W, G, st, ...)                                                                   \
+#define TSFX_LAUNCH_GEOM(KERNEL, W, GS, G, st, ...)                                                               \
     {                                                                                                             \
         if ((G).smem) {                                                                                           \
-            cudaError_t e__ = cudaFuncSetAttribute(KERNEL<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G).smem); \
+            cudaError_t e__ = cudaFuncSetAttribute(KERNEL<W, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G).smem); \
             if (e__ != cudaSuccess) return e__;                                                                   \
         }                                                                                                         \
-        KERNEL<W><<<(G).grid, W * 32, (G).smem, st>>>(__VA_ARGS__);                                               \
+        KERNEL<W, GS><<<(G).grid, W * 32, (G).smem, st>>>(__VA_ARGS__);                                           \
     }
-#define TSFX_DISPATCH(KERNEL, G, st, ...)                                          \
-    switch ((G).wpc) {                                                             \
-        case 8: TSFX_LAUNCH_GEOM(KERNEL, 8, G, st, __VA_ARGS__) break;             \
-        case 4: TSFX_LAUNCH_GEOM(KERNEL, 4, G, st, __VA_ARGS__) break;             \
-        case 2: TSFX_LAUNCH_GEOM(KERNEL, 2, G, st, __VA_ARGS__) break;             \
-        default: TSFX_LAUNCH_GEOM(KERNEL, 1, G, st, __VA_ARGS__) break;            \
+// shared-memory instantiations for 8/4/2/1 warps per CTA, global-scratch instantiations for 4/1
+#define TSFX_DISPATCH(KERNEL, G, st, ...)                                                   \
+    if ((G).gscratch) {                                                                     \
+        if ((G).wpc == 4) TSFX_LAUNCH_GEOM(KERNEL, 4, true, G, st, __VA_ARGS__)             \
+        else TSFX_LAUNCH_GEOM(KERNEL, 1, true, G, st, __VA_ARGS__)                          \
+    } else switch ((G).wpc) {                                                               \
+        case 8: TSFX_LAUNCH_GEOM(KERNEL, 8, false, G, st, __VA_ARGS__) break;               \
+        case 4: TSFX_LAUNCH_GEOM(KERNEL, 4, false, G, st, __VA_ARGS__) break;               \
+        case 2: TSFX_LAUNCH_GEOM(KERNEL, 2, false, G, st, __VA_ARGS__) break;               \
+        default: TSFX_LAUNCH_GEOM(KERNEL, 1, false, G, st, __VA_ARGS__) break;              \
     }
 
 enum Group { G_BASIC = 0, G_SORTED, G_SPECTRAL, G_LA, G_ENTROPY, G_SEQ, G_PEAKS, G_COUNT };
