@@ -130,3 +130,30 @@ def test_rolled_windows_as_views_match_oracle_on_materialised_windows():
     windows = [values[b:b + n].astype(np.float64) for b, n in zip(wb, wl)]
     bad = compare(got, oracle_rows(windows, settings), plan.suffixes)
     assert not bad, bad[:20]
+
+
+def test_distributor_plugin_map_reduce():
+    """The reference's plugin seam (utilities/distribution.py:74-104): extract_features hands the distributor
+    `data` (an iterable of (id, kind, pd.Series)) and `function_kwargs`; B200Distributor must return the triples
+    that `data.pivot` expects without ever calling the Python map function."""
+    from tsfresh_b200.distributor import B200Distributor, is_distributor
+    series = list(synthetic_series(21, 4, 50))
+    data = [(i, "a", pd.Series(s)) for i, s in enumerate(series)] + [(i, "b", pd.Series(s[::-1].copy())) for i, s in enumerate(series)]
+    settings = {"maximum": None, "quantile": [{"q": 0.25}], "linear_trend": [{"attr": "slope"}]}
+    dist = B200Distributor()
+    assert is_distributor(dist)
+
+    def must_not_be_called(*a, **k):
+        raise AssertionError("the Python per-series function must not run")
+
+    triples = dist.map_reduce(must_not_be_called, data=data, chunk_size=None,
+                              function_kwargs=dict(default_fc_parameters=settings, kind_to_fc_parameters={"b": {"minimum": None}},
+                                                   show_warnings=False))
+    dist.close()
+    got = {(i, n): v for i, n, v in triples}
+    assert len(got) == 4 * 3 + 4 * 1
+    for i, s in enumerate(series):
+        assert got[(i, "a__maximum")] == float(s.max())
+        assert got[(i, "a__quantile__q_0.25")] == pytest.approx(np.quantile(s.astype(np.float64), 0.25), rel=1e-12)
+        assert got[(i, "b__minimum")] == float(s.min())
+        assert (i, "b__maximum") not in got
