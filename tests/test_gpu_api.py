@@ -157,3 +157,18 @@ def test_distributor_plugin_map_reduce():
         assert got[(i, "a__quantile__q_0.25")] == pytest.approx(np.quantile(s.astype(np.float64), 0.25), rel=1e-12)
         assert got[(i, "b__minimum")] == float(s.min())
         assert (i, "b__maximum") not in got
+
+
+def test_csr_tsdata_seam():
+    """plugin seam #2: what the reference's ApplyDistributor does with a non-iterable TsData (apply, then pivot)"""
+    from tests.helpers import to_csr
+    from tsfresh_b200.distributor import CsrTsData
+    series = list(synthetic_series(31, 5, 64))
+    values, begin, lens = to_csr(series)
+    data = CsrTsData(values, begin, lens, ids=[3, 5, 8, 13, 21])
+    res = data.apply(None, meta=[("id", "int64"), ("variable", "object"), ("value", "float64")],
+                     default_fc_parameters={"maximum": None, "median": None}, kind_to_fc_parameters=None, show_warnings=False)
+    X = data.pivot(res)
+    assert list(X.columns) == ["value__maximum", "value__median"] and list(X.index) == [3, 5, 8, 13, 21]
+    np.testing.assert_array_equal(X["value__maximum"].to_numpy(), [float(s.max()) for s in series])
+    np.testing.assert_array_equal(X["value__median"].to_numpy(), [float(np.median(s.astype(np.float64))) for s in series])
