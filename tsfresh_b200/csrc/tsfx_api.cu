@@ -22,6 +22,16 @@ int grid_waves(int dflt) {
     if (v < 0) { const char* e = getenv("TSFX_GRID_WAVES"); v = e ? atoi(e) : 0; }
     return v > 0 ? v : dflt;
 }
+int global_above() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TSFX_GLOBAL_ABOVE"); v = e ? atoi(e) : 0; if (v > 227 * 1024 || v < 0) v = 0; }
+    return v;
+}
+int global_ctas_per_sm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TSFX_GLOBAL_CTAS"); v = e ? atoi(e) : 4; if (v < 1 || v > 16) v = 4; }
+    return v;
+}
 }  // namespace tsfx
 
 static int env_streams() {
@@ -358,7 +368,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
     const int staged = P->cum[G_COUNT];
     if (staged == 0) return TSFX_OK;
     CK(ctx->stage.reserve((size_t)R.n_series * staged * sizeof(double)));
-    if (max_len > 1024) CK(ctx->misc.reserve((size_t)1 << 30));      // global working regions for series too long for shared memory
+    CK(ctx->misc.reserve(max_len > 1024 ? ((size_t)1 << 30) : ((size_t)256 << 20)));      // global working regions for series too long for shared memory
     double* const d_final = d_out;
     (void)d_final;
     if (!P->host[G_SPECTRAL].empty()) {      // FFT twiddle table (filled once, on the main stream, before any fork)

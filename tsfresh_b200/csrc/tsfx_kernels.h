@@ -11,14 +11,21 @@ namespace tsfx {
 // CTAs per SM in a launch (each CTA loops over its share of the series).  TSFX_GRID_WAVES overrides the
 // per-kernel default (tuning knob, read once).
 int grid_waves(int dflt);
+int global_above();
+int global_ctas_per_sm();
 
 struct Geometry { int wpc; size_t smem; int grid; unsigned char* gscratch; };
 
 // Chooses warps per CTA / grid for a warp-per-series kernel needing `per` bytes per warp.  Shared memory when it
 // fits (budget = target bytes per CTA so several CTAs stay resident), else the global scratch buffer.
 inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series, int sm_count, unsigned char* gs,
-                          size_t gs_bytes, Geometry* G) {
-    if (per <= 227 * 1024) {
+                          size_t gs_bytes, Geometry* G, size_t prefer_global_above = 227 * 1024) {
+    // Working sets above `prefer_global_above` bytes per warp run from the global (L2-resident) region even though
+    // they would fit in shared memory: measured on B200, the latency-bound PEAKS / SEQ kernels are up to 5x faster
+    // that way at 1024 samples because shared memory would limit them to 2-4 warps per SM (profiles/r1_notes.md).
+    // TSFX_GLOBAL_ABOVE=<bytes> overrides the per-kernel threshold for experiments.
+    const size_t thr = global_above() > 0 ? (size_t)global_above() : prefer_global_above;
+    if (per <= thr && per <= 227 * 1024) {
         size_t w = budget / per;
         int wpc = w >= 8 ? 8 : w >= 4 ? 4 : w >= 2 ? 2 : 1;
         while (wpc > maxw) wpc >>= 1;
@@ -35,7 +42,7 @@ inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series,
     if (max_ctas < 1) { wpc = 1; max_ctas = gs ? gs_bytes / per : 0; }
     if (max_ctas < 1) return false;
     int64_t ctas = (n_series + wpc - 1) / wpc;
-    int64_t cap = (int64_t)sm_count * 4;
+    int64_t cap = (int64_t)sm_count * global_ctas_per_sm();
     if ((int64_t)max_ctas < cap) cap = (int64_t)max_ctas;
     G->wpc = wpc;
     G->smem = 0;
