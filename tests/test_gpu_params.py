@@ -79,3 +79,13 @@ def test_non_default_parameters(ctx, group, kind, length):
     series = list(synthetic_series(500 + length, 24, length, kind))
     bad, *_ = gpu_vs_oracle(ctx, SETTINGS[group], series)
     assert not bad, _report(bad)
+
+
+def test_very_wide_plan(ctx):
+    """thousands of columns in one plan (the assemble pass sizes its shared-memory row buffer accordingly)"""
+    settings = {"fft_coefficient": [{"coeff": k, "attr": a} for a in ("real", "imag", "abs", "angle") for k in range(1200)],
+                "quantile": [{"q": q / 1000.0} for q in range(1001)]}
+    series = list(synthetic_series(3, 6, 300))
+    bad, plan, got, want = gpu_vs_oracle(ctx, settings, series)
+    assert plan.n_cols == 4800 + 1001
+    assert not bad, _report(bad)

@@ -31,17 +31,24 @@ __global__ void __launch_bounds__(WPC * 32) k_assemble(AssembleArgs A, int row_p
     }
 }
 
-cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count) {
-    const int row_pad = (A.ncols + 1) & ~1;
-    constexpr int WPC = 8;
+template <int WPC>
+static cudaError_t launch_assemble_w(const AssembleArgs& A, cudaStream_t st, int sm_count, int row_pad) {
     size_t smem = (size_t)WPC * row_pad * sizeof(double);
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(k_assemble<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t ctas = (A.n_series + WPC - 1) / WPC;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)sm_count * 8));
     k_assemble<WPC><<<grid, WPC * 32, smem, st>>>(A, row_pad);
     return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count) {
+    const int row_pad = (A.ncols + 1) & ~1;
+    const size_t row_bytes = (size_t)row_pad * sizeof(double);
+    if (row_bytes * 8 <= 200 * 1024) return launch_assemble_w<8>(A, st, sm_count, row_pad);
+    if (row_bytes * 2 <= 200 * 1024) return launch_assemble_w<2>(A, st, sm_count, row_pad);
+    if (row_bytes <= 227 * 1024) return launch_assemble_w<1>(A, st, sm_count, row_pad);
+    return cudaErrorInvalidConfiguration;          // more than ~29 000 columns in one plan
 }
 
 }  // namespace tsfx
