@@ -1,12 +1,13 @@
 """Not a test: times the user-facing extract_features(DataFrame) call on BASELINE.json configs[1]
 (EfficientFCParameters, 100 000 series x 256) and prints where the host time goes."""
+import os
 import sys
 import time
 
 import numpy as np
 import pandas as pd
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from tsfresh_b200 import EfficientFCParameters, extract_features  # noqa: E402
 
 N, L = 100_000, 256
