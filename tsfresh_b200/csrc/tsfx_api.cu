@@ -27,9 +27,9 @@ int global_above() {
     if (v < 0) { const char* e = getenv("TSFX_GLOBAL_ABOVE"); v = e ? atoi(e) : 0; if (v > 227 * 1024 || v < 0) v = 0; }
     return v;
 }
-int global_ctas_per_sm() {
+int global_ctas_env() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("TSFX_GLOBAL_CTAS"); v = e ? atoi(e) : 4; if (v < 1 || v > 16) v = 4; }
+    if (v < 0) { const char* e = getenv("TSFX_GLOBAL_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = 0; }
     return v;
 }
 }  // namespace tsfx

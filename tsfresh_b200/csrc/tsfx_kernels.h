@@ -12,14 +12,15 @@ namespace tsfx {
 // per-kernel default (tuning knob, read once).
 int grid_waves(int dflt);
 int global_above();
-int global_ctas_per_sm();
+int global_ctas_env();
 
 struct Geometry { int wpc; size_t smem; int grid; unsigned char* gscratch; };
 
 // Chooses warps per CTA / grid for a warp-per-series kernel needing `per` bytes per warp.  Shared memory when it
 // fits (budget = target bytes per CTA so several CTAs stay resident), else the global scratch buffer.
 inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series, int sm_count, unsigned char* gs,
-                          size_t gs_bytes, Geometry* G, size_t prefer_global_above = 227 * 1024) {
+                          size_t gs_bytes, Geometry* G, size_t prefer_global_above = 227 * 1024,
+                          int global_ctas = 0) {
     // Working sets above `prefer_global_above` bytes per warp run from the global (L2-resident) region even though
     // they would fit in shared memory: measured on B200, the latency-bound PEAKS / SEQ kernels are up to 5x faster
     // that way at 1024 samples because shared memory would limit them to 2-4 warps per SM (profiles/r1_notes.md).
@@ -42,7 +43,8 @@ inline bool plan_geometry(size_t per, size_t budget, int maxw, int64_t n_series,
     if (max_ctas < 1) { wpc = 1; max_ctas = gs ? gs_bytes / per : 0; }
     if (max_ctas < 1) return false;
     int64_t ctas = (n_series + wpc - 1) / wpc;
-    int64_t cap = (int64_t)sm_count * global_ctas_per_sm();
+    // CTAs per SM in global-region mode: TSFX_GLOBAL_CTAS, else the kernel's own choice, else 4
+    int64_t cap = (int64_t)sm_count * (global_ctas_env() > 0 ? global_ctas_env() : global_ctas > 0 ? global_ctas : 4);
     if ((int64_t)max_ctas < cap) cap = (int64_t)max_ctas;
     G->wpc = wpc;
     G->smem = 0;
@@ -150,6 +152,7 @@ struct LaArgs {
 cudaError_t launch_la(const LaArgs& A, int max_len, cudaStream_t st, int sm_count);
 
 struct EntropyArgs {
+    int xpad, bittile;         // padded sample count; 1 = bit-tile counting (default), 0 = pair sweep (TSFX_ENTROPY=pairs)
     SeriesRef R;
     unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used
     size_t gscratch_bytes;
