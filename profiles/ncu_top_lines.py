@@ -15,7 +15,7 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     fname, hdr, agg = None, None, []
     for r in rows:
-        if len(r) >= 2 and r[0] == "File Name":
+        if len(r) >= 2 and r[0] in ("File Name", "File Path"):
             fname = r[1].split("/")[-1]
         elif len(r) > 8 and r[0] == "Line No":
             hdr = {h: i for i, h in enumerate(r)}

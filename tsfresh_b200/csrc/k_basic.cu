@@ -121,11 +121,23 @@ __device__ __forceinline__ Extra extra_pass(const float* xs, const double* xc, i
     return E;
 }
 
-// sum_{t < n-k} xc[t] * xc[t+k]
-__device__ __forceinline__ double lag_product(const double* xc, int n, int k, int lane) {
-    double a = 0.0;
-    for (int i = lane; i + k < n; i += 32) a = fma(xc[i], xc[i + k], a);
-    return wsum(a);
+// lagS[k] = sum_{t < n-k} xc[t] * xc[t+k], k = 0..kmax.  xc is zero beyond n (up to a whole 256-sample chunk plus the
+// largest lag), so no bounds tests: each lane keeps 8 centred samples of a chunk in registers and every lag costs
+// one load + one FMA per sample plus one warp sum.
+__device__ __forceinline__ void lag_products(const double* xc, int n, int kmax, double* lagS, int lane) {
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        double xr[8];
+        const double* xb = xc + i0 + lane;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xr[m] = xb[32 * m];
+        for (int k = 0; k <= kmax; ++k) {
+            double a = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) a = fma(xr[m], xb[32 * m + k], a);
+            a = wsum(a);
+            if (lane == 0) lagS[k] = (i0 == 0) ? a : lagS[k] + a;
+        }
+    }
 }
 
 // numpy histogram bin index for uniform bins (numpy/lib/_histograms_impl.py fast path)
@@ -202,23 +214,26 @@ __device__ __forceinline__ double agg_chunk(const float* xs, int lo, int hi, int
     return f_agg == TSFX_AGG_STD ? sqrt(v) : v;
 }
 
-// linregress(range(k), y[0..k)) with y in shared memory
-__device__ __forceinline__ LinReg linreg_index(const double* y, int k, int lane) {
+// the inputs of linregress(range(k), y[0..k)) with y in shared memory: k, mean(t), mean(y), ssxm, ssym, ssxym
+struct LinSums { double k, tm, ym, sxx, syy, sxy; };
+__device__ __forceinline__ LinSums linreg_sums(const double* y, int k, int lane) {
     double s = 0.0;
     for (int i = lane; i < k; i += 32) s += y[i];
-    double ym = wsum(s) / (double)k;
-    double tm = 0.5 * (double)(k - 1);
+    LinSums L;
+    L.k = (double)k;
+    L.ym = wsum(s) / (double)k;
+    L.tm = 0.5 * (double)(k - 1);
     double sxx = 0.0, syy = 0.0, sxy = 0.0;
     for (int i = lane; i < k; i += 32) {
-        double dt = (double)i - tm, dy = y[i] - ym;
+        double dt = (double)i - L.tm, dy = y[i] - L.ym;
         sxx = fma(dt, dt, sxx);
         syy = fma(dy, dy, syy);
         sxy = fma(dt, dy, sxy);
     }
-    sxx = wsum(sxx) / (double)k;
-    syy = wsum(syy) / (double)k;
-    sxy = wsum(sxy) / (double)k;
-    return m_linregress((double)k, tm, ym, sxx, syy, sxy);
+    L.sxx = wsum(sxx) / (double)k;
+    L.syy = wsum(syy) / (double)k;
+    L.sxy = wsum(sxy) / (double)k;
+    return L;
 }
 
 // leading decimal digit of |v| (shortest-repr digit == true digit for float32-origin values; 0 -> 0)
@@ -338,10 +353,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xc = reinterpret_cast<double*>(base);
-    double* scr = xc + A.npad;
+    double* scr = xc + A.nxc;
     double* lagS = scr + A.nscr;
     double* ST = lagS + A.nlag;                     // ST_COUNT (padded to 32) shared statistics
-    float* xs = reinterpret_cast<float*>(ST + 32);
+    double* altS = ST + 32;                         // 6 regression sums per distinct agg_linear_trend key
+    float* xs = reinterpret_cast<float*>(altS + 6 * A.nalt);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
     // The kernel body is ~250 KB of SASS; warps drifting through different calculators thrash the
@@ -357,12 +373,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
         double* orow = A.out + (size_t)s * A.ncols;
         const double dn = (double)n;
 
+        // zero tail of the centred copy (lag products read up to a whole chunk + the largest lag past n)
+        for (int i = n + lane; i < A.nxc; i += 32) xc[i] = 0.0;
+        __syncwarp();
         if (A.lag_needed > 0) {         // lag products 0..min(lag_needed, n-1)
-            int kmax = min(A.lag_needed, n - 1);
-            for (int k = 0; k <= kmax; ++k) {
-                double v = lag_product(xc, n, k, lane);
-                if (lane == 0) lagS[k] = v;
-            }
+            lag_products(xc, n, min(A.lag_needed, n - 1), lagS, lane);
             __syncwarp();
         }
         if (lane == 0) {
@@ -383,21 +398,43 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                 const Desc d = A.descs[j];
                 orow[d.col] = basic_finisher(d, ST, lagS);
             }
-        // caches for multi-column calculators
-        int lt_key = -1; LinReg lt_fit;
-        bool lin_done = false; LinReg lin_fit;
-        bool pacf_done = false, peaks_done = false;
-
-        for (int j = A.nfin; j < A.nd; ++j) {
+        // The remaining descriptors are sorted by calculator (tsfx_plan_create) and descriptor j writes column j of
+        // the group's staging row.  One trip of the loop consumes a whole run of descriptors of one calculator
+        // when they share a pass over the series (thresholds held in registers, results reduced with REDUX) or
+        // when the per-descriptor work is O(1) after a shared preparation (then one descriptor per lane).
+        for (int j = A.nfin; j < A.nd;) {
             if (WPC > 1) __syncthreads();
             const Desc d = A.descs[j];
+            int run = 0;                    // descriptors j .. j+run-1 have the same calculator
+            for (;;) {
+                const int jj = j + run + lane;
+                const unsigned same = __ballot_sync(FULL, jj < A.nd && A.descs[jj].calc == d.calc);
+                if (same == FULL) { run += 32; continue; }
+                run += __ffs(~same) - 1;
+                break;
+            }
+            int used = 1;                   // descriptors consumed by this trip
+            bool stored = false;            // the case wrote its own columns
             double r = dnan();
             switch (d.calc) {
                 case TSFX_RATIO_BEYOND_R_SIGMA: {
-                    double thr = d.p0 * M.sd;
-                    int c = 0;
-                    for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && fabs(xc[i]) > thr); }
-                    r = (double)c / dn;
+                    constexpr int NB = 5;
+                    used = min(run, NB);
+                    stored = true;
+                    double thr[NB];
+                    int c[NB];
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) { thr[t] = t < used ? A.descs[j + t].p0 * M.sd : dinf(); c[t] = 0; }
+                    for (int i = lane; i < n; i += 32) {
+                        const double v = fabs(xc[i]);
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) c[t] += (v > thr[t]) ? 1 : 0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        const int tot = wsumi(c[t]);
+                        if (t < used && lane == 0 && live) orow[j + t] = (double)tot / dn;
+                    }
                     break;
                 }
                 case TSFX_VALUE_COUNT: {
@@ -440,39 +477,77 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     break;
                 }
                 case TSFX_NUMBER_PEAKS: {
-                    // support radius of every point (largest q with x[i] > x[i-j], x[i] > x[i+j] for all j <= q),
-                    // formed once for the whole run of number_peaks descriptors; number_peaks(n) = #{radius >= n}
+                    // support radius of every point (largest q with x[i] > x[i-k], x[i] > x[i+k] for all k <= q), formed
+                    // once for the run; number_peaks(s) = #{radius >= s}.  Two phases keep the lanes busy: every
+                    // point is walked up to radius CAP1, the few survivors (at least CAP1+1 apart) are then compacted
+                    // and walked on side by side.
+                    used = run;
+                    stored = true;
+                    constexpr int CAP1 = 12;
                     unsigned char* rad = reinterpret_cast<unsigned char*>(scr);
-                    if (!peaks_done) {
-                        int supmax = 1;
-                        for (int jj = j; jj < A.nd && A.descs[jj].calc == TSFX_NUMBER_PEAKS; ++jj) supmax = max(supmax, A.descs[jj].i0);
-                        supmax = min(supmax, 255);
-                        for (int i = lane; i < n; i += 32) {
+                    int* cand = reinterpret_cast<int*>(rad + ((n + 3) & ~3));
+                    int supmax = 1;
+                    for (int t = lane; t < run; t += 32) supmax = max(supmax, A.descs[j + t].i0);
+                    supmax = min(wmaxi(supmax), 255);
+                    int ncand = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        const int i = b0 + lane;
+                        bool more = false;
+                        if (i < n) {
+                            const float v = xs[i];
+                            const int lim = min(min(i, n - 1 - i), supmax), l1 = min(lim, CAP1);
+                            int q = 0;
+                            while (q < l1 && v > xs[i - q - 1] && v > xs[i + q + 1]) ++q;
+                            more = (q == CAP1) && (lim > CAP1);
+                            rad[i] = (unsigned char)q;
+                        }
+                        const unsigned mm = __ballot_sync(FULL, more);
+                        if (more) cand[ncand + __popc(mm & ((1u << lane) - 1u))] = i;
+                        ncand += __popc(mm);
+                    }
+                    __syncwarp();
+                    for (int c0 = 0; c0 < ncand; c0 += 32) {
+                        if (c0 + lane < ncand) {
+                            const int i = cand[c0 + lane];
                             const float v = xs[i];
                             const int lim = min(min(i, n - 1 - i), supmax);
-                            int q = 0;
+                            int q = CAP1;
                             while (q < lim && v > xs[i - q - 1] && v > xs[i + q + 1]) ++q;
                             rad[i] = (unsigned char)q;
                         }
-                        __syncwarp();
-                        peaks_done = true;
                     }
-                    int sup = d.i0, c = 0;
-                    if (sup <= 255) {
-                        for (int b0 = 0; b0 < n; b0 += 32) { int i = b0 + lane; c += wcount(i < n && (int)rad[i] >= sup); }
-                    } else {
-                        for (int b0 = sup; b0 < n - sup; b0 += 32) {
-                            int i = b0 + lane;
-                            bool p = i < n - sup;
-                            if (p) {
-                                float v = xs[i];
-                                for (int q = 1; q <= sup; ++q)
-                                    if (!(v > xs[i - q] && v > xs[i + q])) { p = false; break; }
+                    __syncwarp();
+                    constexpr int NB = 5;
+                    for (int t0 = 0; t0 < run; t0 += NB) {
+                        int sup[NB], c[NB];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) { sup[t] = (t0 + t < run) ? A.descs[j + t0 + t].i0 : 0x7fffffff; c[t] = 0; }
+                        for (int i = lane; i < n; i += 32) {
+                            const int rv = rad[i];
+#pragma unroll
+                            for (int t = 0; t < NB; ++t) c[t] += (rv >= sup[t]) ? 1 : 0;
+                        }
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) {
+                            int tot = wsumi(c[t]);
+                            if (t0 + t < run && sup[t] > 255) {        // supports beyond the radius table: direct test
+                                const int sp = sup[t];
+                                tot = 0;
+                                for (int b0 = sp; b0 < n - sp; b0 += 32) {
+                                    const int i = b0 + lane;
+                                    bool pk = i < n - sp;
+                                    if (pk) {
+                                        const float v = xs[i];
+                                        for (int q = 1; q <= sp; ++q)
+                                            if (!(v > xs[i - q] && v > xs[i + q])) { pk = false; break; }
+                                    }
+                                    tot += wcount(pk);
+                                }
                             }
-                            c += wcount(p);
+                            if (t0 + t < run && lane == 0 && live) orow[j + t0 + t] = (double)tot;
                         }
                     }
-                    r = (double)c;
+                    __syncwarp();
                     break;
                 }
                 case TSFX_AGG_AUTOCORRELATION: {
@@ -512,26 +587,26 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     break;
                 }
                 case TSFX_PARTIAL_AUTOCORRELATION: {
-                    // pacf staged at lagS[nlag_pacf_off ..]; computed once per series by lane 0
+                    // pacf staged at lagS[pacf_off ..], computed once per series by lane 0; one column per lane
+                    used = run;
+                    stored = true;
                     double* pac = lagS + A.pacf_off;
-                    int want = d.i1;
-                    if (!pacf_done) {
-                        if (lane == 0) {
-                            int use = (want >= n / 2) ? n / 2 - 1 : want;
-                            if (n <= 1 || use <= 0) { for (int k = 0; k <= want; ++k) pac[k] = dnan(); }
-                            else {
-                                double* acv = pac + (want + 1);
-                                double* work = acv + (want + 1);
-                                acv[0] = lagS[0] / dn;
-                                for (int k = 1; k <= use; ++k) acv[k] = lagS[k] / (double)(n - k);
-                                m_levinson_pacf(acv, use, pac, work);
-                                for (int k = use + 1; k <= want; ++k) pac[k] = dnan();
-                            }
+                    const int want = d.i1;
+                    if (lane == 0) {
+                        int use = (want >= n / 2) ? n / 2 - 1 : want;
+                        if (n <= 1 || use <= 0) { for (int k = 0; k <= want; ++k) pac[k] = dnan(); }
+                        else {
+                            double* acv = pac + (want + 1);
+                            double* work = acv + (want + 1);
+                            acv[0] = lagS[0] / dn;
+                            for (int k = 1; k <= use; ++k) acv[k] = lagS[k] / (double)(n - k);
+                            m_levinson_pacf(acv, use, pac, work);
+                            for (int k = use + 1; k <= want; ++k) pac[k] = dnan();
                         }
-                        __syncwarp();
-                        pacf_done = true;
                     }
-                    r = pac[d.i0];
+                    __syncwarp();
+                    if (live)
+                        for (int t = lane; t < run; t += 32) orow[j + t] = pac[A.descs[j + t].i0];
                     break;
                 }
                 case TSFX_TIME_REVERSAL_ASYMMETRY_STATISTIC: {
@@ -554,37 +629,66 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     break;
                 }
                 case TSFX_INDEX_MASS_QUANTILE: {
-                    double tot = 0.0;
-                    for (int i = lane; i < n; i += 32) tot += fabs((double)xs[i]);
-                    tot = wsum(tot);
-                    if (tot == 0.0) { r = dnan(); break; }
+                    // cumulative mass fractions once (scr), then every quantile of the run is a count: the fractions
+                    // are non-decreasing, so the first index with fraction >= q is the number of fractions < q
+                    used = run;
+                    stored = true;
                     double carry = 0.0;
-                    int found = -1;
-                    for (int b0 = 0; b0 < n && found < 0; b0 += 32) {
-                        int i = b0 + lane;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        const int i = b0 + lane;
                         double v = i < n ? fabs((double)xs[i]) : 0.0;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {          // inclusive scan
                             double t = __shfl_up_sync(FULL, v, o);
                             if (lane >= o) v += t;
                         }
-                        double cum = carry + v;
-                        unsigned hit = __ballot_sync(FULL, i < n && __ddiv_rn(cum, tot) >= d.p0);
-                        if (hit) found = b0 + __ffs(hit) - 1;
+                        const double cum = carry + v;
+                        if (i < n) scr[i] = cum;
                         carry = __shfl_sync(FULL, cum, 31);
                     }
-                    if (found < 0) found = 0;                       // np.argmax of all-False is 0
-                    r = (double)(found + 1) / dn;
+                    const double tot = carry;
+                    __syncwarp();
+                    if (tot != 0.0)
+                        for (int i = lane; i < n; i += 32) scr[i] = __ddiv_rn(scr[i], tot);
+                    __syncwarp();
+                    constexpr int NB = 4;
+                    for (int t0 = 0; t0 < run; t0 += NB) {
+                        double qv[NB];
+                        int c[NB];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) { qv[t] = (t0 + t < run) ? A.descs[j + t0 + t].p0 : 0.0; c[t] = 0; }
+                        for (int i = lane; i < n; i += 32) {
+                            const double f = scr[i];
+#pragma unroll
+                            for (int t = 0; t < NB; ++t) c[t] += (f < qv[t]) ? 1 : 0;
+                        }
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) {
+                            int found = wsumi(c[t]);
+                            if (found >= n) found = 0;                  // np.argmax of all-False is 0
+                            if (t0 + t < run && lane == 0 && live)
+                                orow[j + t0 + t] = (tot == 0.0) ? dnan() : (double)(found + 1) / dn;
+                        }
+                    }
+                    __syncwarp();
                     break;
                 }
                 case TSFX_ENERGY_RATIO_BY_CHUNKS: {
-                    if (M.sumsq == 0.0) { r = dnan(); break; }
-                    int ns = d.i0, fo = d.i1;
-                    int q = n / ns, rem = n % ns;
-                    int lo = fo * q + min(fo, rem), hi = lo + q + (fo < rem ? 1 : 0);
-                    double a = 0.0;
-                    for (int i = lo + lane; i < hi; i += 32) { double v = xs[i]; a = fma(v, v, a); }
-                    r = wsum(a) / M.sumsq;
+                    used = run;                                         // one segment per lane
+                    stored = true;
+                    for (int t = lane; t < run; t += 32) {
+                        const Desc e = A.descs[j + t];
+                        double rr = dnan();
+                        if (M.sumsq != 0.0) {
+                            const int ns = e.i0, fo = e.i1;
+                            const int q = n / ns, rem = n % ns;
+                            const int lo = fo * q + min(fo, rem), hi = lo + q + (fo < rem ? 1 : 0);
+                            double a = 0.0;
+                            for (int i = lo; i < hi; ++i) { const double v = xs[i]; a = fma(v, v, a); }
+                            rr = a / M.sumsq;
+                        }
+                        if (live) orow[j + t] = rr;
+                    }
                     break;
                 }
                 case TSFX_BINNED_ENTROPY: {
@@ -593,51 +697,88 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     break;
                 }
                 case TSFX_LINEAR_TREND: {
-                    if (!lin_done) {
-                        double tm = 0.5 * (double)(n - 1);
-                        double sxx = 0.0, sxy = 0.0;
-                        for (int i = lane; i < n; i += 32) {
-                            double dt = (double)i - tm;
-                            sxx = fma(dt, dt, sxx);
-                            sxy = fma(dt, xc[i], sxy);
-                        }
-                        sxx = wsum(sxx) / dn;
-                        sxy = wsum(sxy) / dn;
-                        lin_fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
-                        lin_done = true;
+                    used = run;                                         // one attribute per lane
+                    stored = true;
+                    const double tm = 0.5 * (double)(n - 1);
+                    double sxx = 0.0, sxy = 0.0;
+                    for (int i = lane; i < n; i += 32) {
+                        double dt = (double)i - tm;
+                        sxx = fma(dt, dt, sxx);
+                        sxy = fma(dt, xc[i], sxy);
                     }
-                    r = m_linreg_pick(lin_fit, d.attr);
+                    sxx = wsum(sxx) / dn;
+                    sxy = wsum(sxy) / dn;
+                    const LinReg fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
+                    if (live)
+                        for (int t = lane; t < run; t += 32) orow[j + t] = m_linreg_pick(fit, A.descs[j + t].attr);
                     break;
                 }
                 case TSFX_AGG_LINEAR_TREND: {
-                    int cl = d.i0;
-                    if (cl >= n) { r = dnan(); break; }
-                    int key = (cl << 4) | d.i1;
-                    if (key != lt_key) {
-                        int k = (n + cl - 1) / cl;
-                        for (int c = lane; c < k; c += 32) scr[c] = agg_chunk(xs, c * cl, min(n, (c + 1) * cl), d.i1);
-                        __syncwarp();
-                        lt_fit = linreg_index(scr, k, lane);
-                        __syncwarp();
-                        lt_key = key;
+                    // stage A, warp-uniform: the regression sums of every distinct (f_agg, chunk_len) of the run -> altS;
+                    // stage B, one descriptor per lane: linregress of its key's sums and the attribute it asks for
+                    used = run;
+                    stored = true;
+                    int slot = 0, key_prev = -1;
+                    for (int t = 0; t < run; ++t) {
+                        const int cl = A.descs[j + t].i0, fa = A.descs[j + t].i1;
+                        const int key = (cl << 4) | fa;
+                        if (key == key_prev) continue;
+                        key_prev = key;
+                        LinSums L;
+                        L.k = -1.0;                                     // chunk_len >= n: NaN
+                        L.tm = L.ym = L.sxx = L.syy = L.sxy = 0.0;
+                        if (cl < n) {
+                            const int k = (n + cl - 1) / cl;
+                            for (int c = lane; c < k; c += 32) scr[c] = agg_chunk(xs, c * cl, min(n, (c + 1) * cl), fa);
+                            __syncwarp();
+                            L = linreg_sums(scr, k, lane);
+                            __syncwarp();
+                        }
+                        if (lane == 0 && slot < A.nalt) {
+                            double* S = altS + 6 * slot;
+                            S[0] = L.k; S[1] = L.tm; S[2] = L.ym; S[3] = L.sxx; S[4] = L.syy; S[5] = L.sxy;
+                        }
+                        ++slot;
                     }
-                    r = m_linreg_pick(lt_fit, d.attr);
+                    __syncwarp();
+                    int base_slot = -1, last_key = -1;                  // slot of the descriptor before this batch of 32
+                    for (int t0 = 0; t0 < run; t0 += 32) {
+                        const int t = t0 + lane;
+                        const bool ok = t < run;
+                        const Desc e = A.descs[j + (ok ? t : 0)];
+                        const int key = (e.i0 << 4) | e.i1;
+                        int prev = __shfl_up_sync(FULL, key, 1);
+                        if (lane == 0) prev = last_key;
+                        const unsigned chg = __ballot_sync(FULL, ok && key != prev);
+                        const int my_slot = base_slot + __popc(chg & (0xffffffffu >> (31 - lane)));
+                        if (ok && live) {
+                            const double* S = altS + 6 * my_slot;
+                            double rr = dnan();
+                            if (S[0] >= 0.0) rr = m_linreg_pick(m_linregress(S[0], S[1], S[2], S[3], S[4], S[5]), e.attr);
+                            orow[j + t] = rr;
+                        }
+                        base_slot += __popc(chg);
+                        last_key = __shfl_sync(FULL, key, 31);
+                    }
+                    __syncwarp();
                     break;
                 }
                 case TSFX_BENFORD_CORRELATION: {
                     int cnt[9];
 #pragma unroll
                     for (int q = 0; q < 9; ++q) cnt[q] = 0;
-                    for (int b0 = 0; b0 < n; b0 += 32) {
-                        int i = b0 + lane;
-                        int dg = i < n ? leading_digit(xs[i], A.dec) : -1;
+                    for (int i = lane; i < n; i += 32) {
+                        const int dg = leading_digit(xs[i], A.dec);
 #pragma unroll
-                        for (int q = 0; q < 9; ++q) cnt[q] += wcount(dg == q + 1);
+                        for (int q = 0; q < 9; ++q) cnt[q] += (dg == q + 1) ? 1 : 0;
                     }
-                    // np.corrcoef(benford, observed)[0, 1]
-                    double ben[9], obs[9], mb = 0.0, mo = 0.0;
+                    // np.corrcoef(benford, observed)[0, 1];  benford[q] = log10(1 + 1/(q+1))
+                    const double ben[9] = {0.30102999566398120, 0.17609125905568124, 0.12493873660829993,
+                                           0.09691001300805642, 0.07918124604762482, 0.06694678963061322,
+                                           0.05799194697768673, 0.05115252244738129, 0.04575749056067514};
+                    double obs[9], mb = 0.0, mo = 0.0;
 #pragma unroll
-                    for (int q = 0; q < 9; ++q) { ben[q] = log10(1.0 + 1.0 / (double)(q + 1)); obs[q] = (double)cnt[q] / dn; mb += ben[q]; mo += obs[q]; }
+                    for (int q = 0; q < 9; ++q) { obs[q] = (double)wsumi(cnt[q]) / dn; mb += ben[q]; mo += obs[q]; }
                     mb /= 9.0; mo /= 9.0;
                     double sbb = 0.0, soo = 0.0, sbo = 0.0;
 #pragma unroll
@@ -651,7 +792,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                 case TSFX_CONST_NAN:
                 default: r = dnan(); break;
             }
-            if (lane == 0 && live) orow[d.col] = r;
+            if (!stored && lane == 0 && live) orow[j] = r;
+            j += used;
         }
         __syncwarp();
     }
@@ -663,7 +805,8 @@ bool basic_finisher_calc(int calc) { return basic_is_finisher(calc); }
 cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     BasicArgs A = A0;
     A.npad = (max_len + 3) & ~3;
-    size_t per = (size_t)A.npad * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + 32 * 8 + (size_t)A.npad * 4;
+    A.nxc = ((max_len + 255) / 256) * 256 + ((A.lag_needed + 1) & ~1);      // centred copy + zero tail for the lag products
+    size_t per = (size_t)A.nxc * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + 32 * 8 + (size_t)A.nalt * 48 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     Geometry G;

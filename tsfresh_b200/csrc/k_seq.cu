@@ -18,8 +18,8 @@ namespace tsfx {
 #define LZ_LANES 8
 
 struct SeqLayout {
-    int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride;
-    int off_rowsf, off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs;   // byte offsets
+    int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride, nxd;
+    int off_rowsf, off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs, off_xd;   // byte offsets
 };
 
 // ---------------------------------------------------------------------------- Lempel-Ziv
@@ -57,17 +57,28 @@ __device__ __forceinline__ void warp_bitonic_sort_u32(unsigned* s, int m, int la
 }
 
 // ---------------------------------------------------------------------------- find_peaks_cwt pieces
-// value of cwt row (width w) at column i: convolve(x, ricker(min(10w, n), w), mode="same")[i]
-__device__ __forceinline__ double cwt_value(const float* xs, int n, const double* hw, int npts, int i) {
+// cwt row of width w: dst[i] = convolve(x, ricker(npts, w), mode="same")[i] = sum_u h[u] x[i + c0 - u], c0 = (npts-1)/2.
+// xd is the series as float64 with TSFX_MAXW_PTS zeros in front and zeros up to a whole 256-sample chunk (+ the
+// same margin) behind, so no tap needs a bounds test.  Each lane forms 8 outputs (i = lane + 32 m) at once: one
+// broadcast load of the tap serves all of them, i.e. ~2.4 instructions per output tap instead of ~5.5.
+__device__ __forceinline__ void cwt_row(const double* xd, int n, const double* hw, int npts, double* dst, int lane) {
     const int c0 = (npts - 1) / 2;
-    // same[i] = sum_t x[t] h[i + c0 - t], 0 <= i + c0 - t < npts
-    int t_lo = i + c0 - (npts - 1);
-    if (t_lo < 0) t_lo = 0;
-    int t_hi = i + c0;
-    if (t_hi > n - 1) t_hi = n - 1;
-    double a = 0.0;
-    for (int t = t_lo; t <= t_hi; ++t) a = fma((double)xs[t], hw[i + c0 - t], a);
-    return a;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        double acc[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+        const double* xb = xd + TSFX_MAXW_PTS + i0 + lane + c0;
+        for (int u = 0; u < npts; ++u) {
+            const double h = hw[u];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m] = fma(xb[32 * m - u], h, acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int i = i0 + lane + 32 * m;
+            if (i < n) dst[i] = acc[m];
+        }
+    }
 }
 
 __device__ __forceinline__ void ricker_fill(double* hw, int npts, int w, int lane) {
@@ -92,6 +103,17 @@ __device__ __forceinline__ double percentile10(const double* win, int wlen) {
     const int i = (int)idx;
     double pv = 0.0, v0 = 0.0, v1 = 0.0;
     int pi = -1;
+    if (i <= 1) {                       // windows of up to 20 samples: the three smallest in one pass
+        double m0 = dinf(), m1 = dinf(), m2 = dinf();
+        for (int a = 0; a < wlen; ++a) {
+            const double va = win[a];
+            if (va < m0) { m2 = m1; m1 = m0; m0 = va; }
+            else if (va < m1) { m2 = m1; m1 = va; }
+            else if (va < m2) m2 = va;
+        }
+        v0 = i == 0 ? m0 : m1;
+        v1 = i == 0 ? m1 : m2;
+    } else
     for (int r = 0; r <= i + 1 && r < wlen; ++r) {
         double bv = 0.0;
         int bi = -1;
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     short* lines = reinterpret_cast<short*>(base + Y.off_lines);
     int* colmap = reinterpret_cast<int*>(base + Y.off_map);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
+    double* xd = reinterpret_cast<double*>(base + Y.off_xd);               // zero-padded float64 copy for the convolutions
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
     const int LCAP = Y.npad + Y.npad / 2 + 32;   // alive (<= maxima of the two previous rows <= n) + new in this row (<= n/2)
 
@@ -325,12 +348,17 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
             const Desc d0 = A.descs[j];
             if (d0.calc == TSFX_NUMBER_CWT_PEAKS) {
                 if (!cwt_ready) {
+                    for (int p = lane; p < Y.nxd; p += 32) {
+                        const int t = p - TSFX_MAXW_PTS;
+                        xd[p] = (t >= 0 && t < n) ? (double)xs[t] : 0.0;
+                    }
+                    __syncwarp();
                     // all rows 1..cwt_n once (kept in shared memory) + local-maximum bit masks per row
                     for (int w = 1; w <= Y.cwt_n; ++w) {
                         const int npts = min(10 * w, n);
                         ricker_fill(hw, npts, w, lane);
                         double* dst = (w == 1) ? row0 : tmp;
-                        for (int i = lane; i < n; i += 32) dst[i] = cwt_value(xs, n, hw, npts, i);
+                        cwt_row(xd, n, hw, npts, dst, lane);
                         __syncwarp();
                         unsigned* bits = maxbits + (size_t)(w - 1) * Y.nwords;
                         for (int b0 = 0; b0 < n; b0 += 32) {
@@ -530,6 +558,9 @@ cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm
     Y.off_map = (int)off;   off += (size_t)A.npad * 4;
     off = (off + 15) & ~(size_t)15;
     Y.off_xs = (int)off;    off += (size_t)A.npad * 4;
+    off = (off + 15) & ~(size_t)15;
+    Y.nxd = ((max_len + 255) / 256) * 256 + 2 * TSFX_MAXW_PTS;
+    Y.off_xd = (int)off;    off += (size_t)Y.nxd * 8;
     size_t per = (off + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     Geometry G;

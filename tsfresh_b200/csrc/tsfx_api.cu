@@ -409,6 +409,15 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 A.pacf_off = P->lag_needed + 1;
                 A.nlag = even(P->lag_needed + 1 + pac);
                 A.nscr = even(std::max(std::max(max_len, 64), (P->basic_bins + 1) / 2));
+                A.nalt = 0;
+                {
+                    int prev = -1;
+                    for (const Desc& q : P->host[g])
+                        if (q.calc == TSFX_AGG_LINEAR_TREND) {
+                            const int key = (q.i0 << 4) | q.i1;
+                            if (key != prev) { ++A.nalt; prev = key; }
+                        }
+                }
                 A.dec = ctx->d_dec;
                 e = launch_basic(A, max_len, gs, ctx->sm_count);
                 break;

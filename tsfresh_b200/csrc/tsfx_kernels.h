@@ -99,6 +99,7 @@ struct BasicArgs {
     double* out;
     int ncols;
     int npad, nscr, nlag, bytes_per_warp;   // shared-memory carve-up (doubles / doubles / doubles / bytes)
+    int nxc, nalt;       // doubles of the centred copy incl. its zero tail; distinct agg_linear_trend (f_agg, chunk_len) keys
     int nfin;            // the first nfin descriptors are O(1) "finishers" (see k_basic.cu)
     int lag_needed;      // largest lag product any descriptor reads (0 = none)
     int pacf_off;        // offset (doubles) of the pacf staging area inside lagS
