@@ -532,7 +532,7 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     size_t per = (off + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     Geometry G;
-    if (!plan_geometry(per, 72 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G, 40 * 1024, 8)) return cudaErrorInvalidConfiguration;
+    if (!plan_geometry(per, 72 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G, 16 * 1024, 8)) return cudaErrorInvalidConfiguration;
     A.gscratch = G.gscratch;
     TSFX_DISPATCH(k_seq, G, st, A, Y)
     return cudaGetLastError();

@@ -176,15 +176,23 @@ __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt,
         }
     }
     __syncwarp();
+    // bin means of the non-empty bins, compacted in bin order (32 bins per round; a round only overwrites slots
+    // at or below the bins it has already read)
     int k = 0;
-    if (lane == 0) {
-        for (int b = 0; b < r; ++b) {
-            double c = cnt[b];
-            if (c > 0.0) { double mx = sx[b] / c, my = sy[b] / c; sx[k] = mx; sy[k] = my; ++k; }
+    for (int b0 = 0; b0 < r; b0 += 32) {
+        const int b = b0 + lane;
+        const double c = b < r ? cnt[b] : 0.0;
+        double mx = 0.0, my = 0.0;
+        if (c > 0.0) { mx = sx[b] / c; my = sy[b] / c; }
+        const unsigned full = __ballot_sync(FULL, c > 0.0);
+        __syncwarp();
+        if (c > 0.0) {
+            const int dst = k + __popc(full & ((1u << lane) - 1u));
+            sx[dst] = mx; sy[dst] = my;
         }
+        k += __popc(full);
+        __syncwarp();
     }
-    k = __shfl_sync(FULL, k, 0);
-    __syncwarp();
     int ok = 0;
     if (k >= 4) ok = warp_polyfit3(sx, sy, k, coef, lane) ? 1 : 0;
     else {
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* scr = reinterpret_cast<double*>(base);
-    float* xs = reinterpret_cast<float*>(scr + A.nscr);
+    float* xs = reinterpret_cast<float*>(scr + A.nscr + 5 * A.ncq + (A.ncq & 1));
     float* srt = xs + A.npad;
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
@@ -231,30 +239,22 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
         const double med = (n & 1) ? (double)srt[n >> 1] : 0.5 * ((double)srt[(n >> 1) - 1] + (double)srt[n >> 1]);
         double* orow = A.out + (size_t)s * A.ncols;
 
-        bool uniq_done = false; Uniq U;
-        // change_quantiles cache
-        double cq_ql = -1.0, cq_qh = -1.0;
-        double cq_mean0 = 0.0, cq_mean1 = 0.0, cq_var0 = 0.0, cq_var1 = 0.0; int cq_cnt = 0;
-        // friedrich cache
-        int fr_r = -1; bool fr_ok = false;
+        int fr_r = -1; bool fr_ok = false;          // friedrich cache
         double* coef = scr + (A.nscr - 8);
+        double* cqS = scr + A.nscr;                 // 5 doubles per distinct change_quantiles corridor
 
-        for (int j = 0; j < A.nd; ++j) {
-            if (WPC > 1) __syncthreads();
-            const Desc d = A.descs[j];
-            double r = dnan();
-            switch (d.calc) {
-                case TSFX_MEDIAN: r = med; break;
-                case TSFX_QUANTILE: r = m_quantile_sorted(srt, n, d.p0); break;
-                case TSFX_SYMMETRY_LOOKING: r = (fabs(mean - med) < d.p0 * (vmax - vmin)) ? 1.0 : 0.0; break;
-                case TSFX_HAS_DUPLICATE:
-                case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
-                case TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS:
-                case TSFX_SUM_OF_REOCCURRING_VALUES:
-                case TSFX_SUM_OF_REOCCURRING_DATA_POINTS:
-                case TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH: {
-                    if (!uniq_done) { U = unique_pass(srt, n, lane); uniq_done = true; }
+        // O(1) "finishers" (the first A.nfin descriptors): order statistics and the unique-value counts, one
+        // descriptor per lane
+        if (A.nfin > 0) {
+            const Uniq U = unique_pass(srt, n, lane);
+            if (live)
+                for (int j = lane; j < A.nfin; j += 32) {
+                    const Desc d = A.descs[j];
+                    double r = dnan();
                     switch (d.calc) {
+                        case TSFX_MEDIAN: r = med; break;
+                        case TSFX_QUANTILE: r = m_quantile_sorted(srt, n, d.p0); break;
+                        case TSFX_SYMMETRY_LOOKING: r = (fabs(mean - med) < d.p0 * (vmax - vmin)) ? 1.0 : 0.0; break;
                         case TSFX_HAS_DUPLICATE: r = U.any_dup ? 1.0 : 0.0; break;
                         case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
                             r = (double)U.n_reocc_values / (double)U.n_unique; break;
@@ -262,10 +262,29 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
                             r = (double)U.n_reocc_points / dn; break;
                         case TSFX_SUM_OF_REOCCURRING_VALUES: r = U.sum_reocc_values; break;
                         case TSFX_SUM_OF_REOCCURRING_DATA_POINTS: r = U.sum_reocc_points; break;
-                        default: r = (double)U.n_unique / dn; break;
+                        case TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH: r = (double)U.n_unique / dn; break;
+                        default: break;
                     }
-                    break;
+                    orow[j] = r;
                 }
+        }
+
+        // remaining descriptors: sorted by calculator, descriptor j writes column j; one trip per run (see k_basic.cu)
+        for (int j = A.nfin; j < A.nd;) {
+            if (WPC > 1) __syncthreads();
+            const Desc d = A.descs[j];
+            int run = 0;
+            for (;;) {
+                const int jj = j + run + lane;
+                const unsigned same = __ballot_sync(FULL, jj < A.nd && A.descs[jj].calc == d.calc);
+                if (same == FULL) { run += 32; continue; }
+                run += __ffs(~same) - 1;
+                break;
+            }
+            int used = 1;
+            bool stored = false;
+            double r = dnan();
+            switch (d.calc) {
                 case TSFX_MEAN_N_ABSOLUTE_MAX: {
                     int k = d.i0;
                     if (n <= k) { r = dnan(); break; }
@@ -281,38 +300,74 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
                     break;
                 }
                 case TSFX_CHANGE_QUANTILES: {
-                    if (d.p0 >= d.p1) { r = 0.0; break; }
-                    if (!(d.p0 == cq_ql && d.p1 == cq_qh)) {
-                        // one corridor = two passes that serve all four (isabs, f_agg) columns:
-                        // pass 1: count, sum d, sum |d| ; pass 2: centred squares of d and of |d|
-                        cq_ql = d.p0; cq_qh = d.p1;
-                        const double lo = m_quantile_sorted(srt, n, d.p0), hi = m_quantile_sorted(srt, n, d.p1);
-                        int c = 0;
-                        double s1 = 0.0, s1a = 0.0;
-                        for (int i = lane; i + 1 < n; i += 32) {
-                            const double a = (double)xs[i], b = (double)xs[i + 1];
-                            if (a >= lo && a <= hi && b >= lo && b <= hi) { const double dx = b - a; s1 += dx; s1a += fabs(dx); ++c; }
-                        }
-                        cq_cnt = wsumi(c);
-                        cq_mean0 = wsum(s1) / (double)cq_cnt;
-                        cq_mean1 = wsum(s1a) / (double)cq_cnt;
-                        double q2 = 0.0, q2a = 0.0;
-                        if (cq_cnt > 0)
+                    // stage A, warp-uniform: every distinct corridor (ql, qh) of the run -> count, mean and variance of
+                    // the changes and of their magnitudes (two passes serve all four (isabs, f_agg) columns);
+                    // stage B: one descriptor per lane picks its column
+                    used = run;
+                    stored = true;
+                    int slot = 0;
+                    double pl = -1.0, ph = -1.0;
+                    for (int t = 0; t < run; ++t) {
+                        const double ql = A.descs[j + t].p0, qh = A.descs[j + t].p1;
+                        if (ql == pl && qh == ph) continue;
+                        pl = ql; ph = qh;
+                        int cnt = 0;
+                        double mean0 = 0.0, mean1 = 0.0, var0 = 0.0, var1 = 0.0;
+                        if (ql < qh) {
+                            const double lo = m_quantile_sorted(srt, n, ql), hi = m_quantile_sorted(srt, n, qh);
+                            int c = 0;
+                            double s1 = 0.0, s1a = 0.0;
                             for (int i = lane; i + 1 < n; i += 32) {
                                 const double a = (double)xs[i], b = (double)xs[i + 1];
-                                if (a >= lo && a <= hi && b >= lo && b <= hi) {
-                                    const double dx = b - a, e = dx - cq_mean0, ea = fabs(dx) - cq_mean1;
-                                    q2 = fma(e, e, q2);
-                                    q2a = fma(ea, ea, q2a);
-                                }
+                                if (a >= lo && a <= hi && b >= lo && b <= hi) { const double dx = b - a; s1 += dx; s1a += fabs(dx); ++c; }
                             }
-                        cq_var0 = wsum(q2) / (double)cq_cnt;
-                        cq_var1 = wsum(q2a) / (double)cq_cnt;
+                            cnt = wsumi(c);
+                            mean0 = wsum(s1) / (double)cnt;
+                            mean1 = wsum(s1a) / (double)cnt;
+                            double q2 = 0.0, q2a = 0.0;
+                            if (cnt > 0)
+                                for (int i = lane; i + 1 < n; i += 32) {
+                                    const double a = (double)xs[i], b = (double)xs[i + 1];
+                                    if (a >= lo && a <= hi && b >= lo && b <= hi) {
+                                        const double dx = b - a, e = dx - mean0, ea = fabs(dx) - mean1;
+                                        q2 = fma(e, e, q2);
+                                        q2a = fma(ea, ea, q2a);
+                                    }
+                                }
+                            var0 = wsum(q2) / (double)cnt;
+                            var1 = wsum(q2a) / (double)cnt;
+                        }
+                        if (lane == 0 && slot < A.ncq) {
+                            double* S = cqS + 5 * slot;
+                            S[0] = (double)cnt; S[1] = mean0; S[2] = mean1; S[3] = var0; S[4] = var1;
+                        }
+                        ++slot;
                     }
-                    if (cq_cnt == 0) { r = 0.0; break; }
-                    const double mu = d.i0 ? cq_mean1 : cq_mean0, va = d.i0 ? cq_var1 : cq_var0;
-                    if (d.attr == TSFX_AGG_MEAN) r = mu;
-                    else r = (d.attr == TSFX_AGG_STD) ? sqrt(va) : va;
+                    __syncwarp();
+                    int base_slot = -1;
+                    double last_l = -1.0, last_h = -1.0;
+                    for (int t0 = 0; t0 < run; t0 += 32) {
+                        const int t = t0 + lane;
+                        const bool ok = t < run;
+                        const Desc e = A.descs[j + (ok ? t : 0)];
+                        double prev_l = __shfl_up_sync(FULL, e.p0, 1), prev_h = __shfl_up_sync(FULL, e.p1, 1);
+                        if (lane == 0) { prev_l = last_l; prev_h = last_h; }
+                        const unsigned chg = __ballot_sync(FULL, ok && !(e.p0 == prev_l && e.p1 == prev_h));
+                        const int my_slot = base_slot + __popc(chg & (0xffffffffu >> (31 - lane)));
+                        if (ok && live) {
+                            const double* S = cqS + 5 * my_slot;
+                            double rr = 0.0;                             // ql >= qh or an empty corridor: 0
+                            if (S[0] > 0.0) {
+                                const double mu = e.i0 ? S[2] : S[1], va = e.i0 ? S[4] : S[3];
+                                rr = (e.attr == TSFX_AGG_MEAN) ? mu : (e.attr == TSFX_AGG_STD) ? sqrt(va) : va;
+                            }
+                            orow[j + t] = rr;
+                        }
+                        base_slot += __popc(chg);
+                        last_l = __shfl_sync(FULL, e.p0, 31);
+                        last_h = __shfl_sync(FULL, e.p1, 31);
+                    }
+                    __syncwarp();
                     break;
                 }
                 case TSFX_FRIEDRICH_COEFFICIENTS:
@@ -329,9 +384,21 @@ __global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
                 }
                 default: break;
             }
-            if (lane == 0 && live) orow[d.col] = r;
+            if (!stored && lane == 0 && live) orow[j] = r;
+            j += used;
         }
         __syncwarp();
+    }
+}
+
+bool sorted_finisher_calc(int calc) {
+    switch (calc) {
+        case TSFX_MEDIAN: case TSFX_QUANTILE: case TSFX_SYMMETRY_LOOKING: case TSFX_HAS_DUPLICATE:
+        case TSFX_PERCENTAGE_OF_REOCCURRING_VALUES_TO_ALL_VALUES:
+        case TSFX_PERCENTAGE_OF_REOCCURRING_DATAPOINTS_TO_ALL_DATAPOINTS:
+        case TSFX_SUM_OF_REOCCURRING_VALUES: case TSFX_SUM_OF_REOCCURRING_DATA_POINTS:
+        case TSFX_RATIO_VALUE_NUMBER_TO_TIME_SERIES_LENGTH: return true;
+        default: return false;
     }
 }
 
@@ -342,7 +409,7 @@ cudaError_t launch_sorted(const SortedArgs& A0, int max_len, cudaStream_t st, in
     while (p2 < max_len) p2 <<= 1;
     A.npow2 = std::max(p2, 4);
     A.nscr = (A.nscr + 1) & ~1;
-    size_t per = (size_t)A.nscr * 8 + (size_t)A.npad * 4 + (size_t)A.npow2 * 4;
+    size_t per = (size_t)A.nscr * 8 + (size_t)(5 * A.ncq + (A.ncq & 1)) * 8 + (size_t)A.npad * 4 + (size_t)A.npow2 * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
     Geometry G;

@@ -85,6 +85,7 @@ struct tsfx_plan {
     Desc* dev[G_COUNT] = {nullptr};
     int32_t* d_final_col = nullptr;   // final column of every staged column, groups concatenated
     int basic_nfin = 0;               // leading "finisher" descriptors of the BASIC group
+    int sorted_nfin = 0;              // same for the SORTED group
     int spectral_nfft = 0;            // leading fft_coefficient descriptors of the SPECTRAL group
     int cum[G_COUNT + 1] = {0};
     int ncols = 0;
@@ -285,6 +286,10 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
                 const bool fa = basic_finisher_calc(a.calc), fb = basic_finisher_calc(b.calc);
                 if (fa != fb) return fa;
             }
+            if (g == G_SORTED) {
+                const bool fa = sorted_finisher_calc(a.calc), fb = sorted_finisher_calc(b.calc);
+                if (fa != fb) return fa;
+            }
             if (g == G_SPECTRAL) {            // fft_coefficient first, grouped by attribute
                 const bool fa = a.calc == TSFX_FFT_COEFFICIENT, fb = b.calc == TSFX_FFT_COEFFICIENT;
                 if (fa != fb) return fa;
@@ -300,6 +305,8 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
         });
         if (g == G_BASIC)
             for (const Desc& d : P->host[g]) P->basic_nfin += basic_finisher_calc(d.calc) ? 1 : 0;
+        if (g == G_SORTED)
+            for (const Desc& d : P->host[g]) P->sorted_nfin += sorted_finisher_calc(d.calc) ? 1 : 0;
         if (g == G_SPECTRAL)
             for (const Desc& d : P->host[g]) P->spectral_nfft += (d.calc == TSFX_FFT_COEFFICIENT) ? 1 : 0;
         P->cum[g + 1] = P->cum[g] + (int)P->host[g].size();
@@ -426,6 +433,13 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 SortedArgs A;
                 A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = even(4 * (P->friedrich_r + 2) + 16);
+                A.nfin = P->sorted_nfin;
+                A.ncq = 0;
+                {
+                    double pl = -1.0, ph = -1.0;
+                    for (const Desc& q : P->host[g])
+                        if (q.calc == TSFX_CHANGE_QUANTILES && !(q.p0 == pl && q.p1 == ph)) { ++A.ncq; pl = q.p0; ph = q.p1; }
+                }
                 e = launch_sorted(A, max_len, gs, ctx->sm_count);
                 break;
             }

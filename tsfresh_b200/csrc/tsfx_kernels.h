@@ -106,7 +106,8 @@ struct BasicArgs {
     const double* dec;   // device table d*10^k, k = TSFX_DEC_MIN..TSFX_DEC_MAX, 9 per decade
 };
 cudaError_t launch_basic(const BasicArgs& A, int max_len, cudaStream_t st, int sm_count);
-bool basic_finisher_calc(int calc);     // host: is this calculator evaluated by the lane-parallel finisher stage?
+bool basic_finisher_calc(int calc);
+bool sorted_finisher_calc(int calc);    // same for the SORTED group     // host: is this calculator evaluated by the lane-parallel finisher stage?
 
 struct SortedArgs {
     SeriesRef R;
@@ -117,6 +118,7 @@ struct SortedArgs {
     double* out;
     int ncols;
     int npad, npow2, nscr, bytes_per_warp;
+    int nfin, ncq;       // leading O(1) descriptors (lane-parallel); distinct change_quantiles corridors
 };
 cudaError_t launch_sorted(const SortedArgs& A, int max_len, cudaStream_t st, int sm_count);
 
