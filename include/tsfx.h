@@ -48,6 +48,15 @@ extern "C" {
 #define TSFX_FLAG_DEVICE_PTRS 1u /* values/begin/len/out are device pointers; async on ctx stream */
 #define TSFX_FLAG_TIMING 2u      /* record CUDA events around every kernel group (tsfx_get_timings) */
 #define TSFX_FLAG_NO_NAN_CHECK 4u
+#define TSFX_FLAG_IMPUTE 8u      /* extract calls: impute the feature matrix on the device before it is returned
+                                  * (extract_features(impute_function=impute), extraction.py:179-181, 286-287) */
+#define TSFX_FLAG_ALL_MEDIANS 16u /* tsfx_impute: compute every column's median, not only those a NaN needs */
+
+/* tsfx_impute modes (tsfresh/utilities/dataframe_functions.py) */
+#define TSFX_IMPUTE_RANGE 0      /* impute :49-78: +inf -> max, -inf -> min, NaN -> median of the finite values */
+#define TSFX_IMPUTE_ZERO 1       /* impute_dataframe_zero :81-101: every non-finite value -> 0 */
+#define TSFX_IMPUTE_GIVEN 2      /* impute_dataframe_range :104-167: replacement values supplied by the caller */
+#define TSFX_IMPUTE_STATS 3      /* get_range_values_per_column :170-212: statistics only, matrix untouched */
 
 /* calculator ids: one per reference calculator (feature_calculators.py line in the comment) */
 enum tsfx_calc {
@@ -200,6 +209,16 @@ int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, int64_t n_se
                           int32_t rolling_direction, int32_t max_timeshift, int32_t min_timeshift,
                           int64_t* win_begin, int32_t* win_len, int64_t* win_parent,
                           int32_t* win_end_index, int64_t capacity);
+
+/* Column-wise imputation of a row-major float64 matrix [n_rows x n_cols], in place (replaces the reference's
+ * tsfresh.utilities.dataframe_functions.impute / impute_dataframe_zero / impute_dataframe_range /
+ * get_range_values_per_column, dataframe_functions.py:49-212, on the matrix extract_features returns).
+ * `matrix` is a host pointer (copied to the device and back) or, with TSFX_FLAG_DEVICE_PTRS, a device pointer.
+ * col_stats: host array of 3*n_cols doubles laid out min | max | median -- output for RANGE / STATS (may be NULL
+ * for RANGE), input for GIVEN, ignored for ZERO.  Columns without any finite value report 0 for all three.
+ * Without TSFX_FLAG_ALL_MEDIANS the median of a column that holds no NaN is not computed and reported as NaN. */
+int tsfx_impute(tsfx_ctx* ctx, double* matrix, int64_t n_rows, int32_t n_cols, int32_t mode, double* col_stats,
+                uint32_t flags);
 
 /* Per-kernel-group device time (ms) of the last extract call made with TSFX_FLAG_TIMING.
  * names_out[i] points at a static string.  Returns the number of groups written (<= cap). */

@@ -129,3 +129,14 @@ def test_fixture80_end_to_end_values():
                        ("b__sum_values", [757, 695]), ("b__minimum", [3, 1]), ("b__abs_energy", [36619, 35483]),
                        ("b__mean", [37.85, 34.75]), ("b__median", [39.5, 28.0])):
         np.testing.assert_allclose(ref[:, cols.index(name)], want)
+
+
+def test_oracle_impute_reproduces_reference_golden():
+    """tests/golden/impute.npz (oracle/make_golden_impute.py, unmodified reference) -- bit-exact."""
+    from oracle import impute as oi
+    g = np.load(os.path.join(G, "impute.npz"))
+    m = g["input"]
+    assert np.array_equal(oi.range_values(m), g["stats"])
+    assert np.array_equal(oi.impute(m), g["imputed"])
+    assert np.array_equal(oi.impute_zero(m), g["zero"])
+    assert np.isfinite(g["imputed"]).all()

@@ -61,3 +61,25 @@ def test_oracle_matches_reference_short_series():
     mine = oracle_rows([s.astype(np.float64) for s in series], settings)
     bad = compare(mine, X.to_numpy(dtype=np.float64), plan.suffixes, rtol=1e-12)
     assert not bad, bad[:20]
+
+
+def test_oracle_impute_matches_reference():
+    """oracle/impute.py against tsfresh.utilities.dataframe_functions (:49-212) on random matrices."""
+    ref_shim.load()
+    from tsfresh.utilities import dataframe_functions as rdf
+    from oracle import impute as oi
+    from oracle.make_golden_impute import make_input
+    for seed, rows, cols in ((1, 50, 9), (2, 201, 14), (3, 17, 11)):
+        m = make_input(seed, rows, cols) if cols >= 10 else np.random.default_rng(seed).standard_normal((rows, cols))
+        names = ["c%d" % i for i in range(m.shape[1])]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cmax, cmin, cmed = rdf.get_range_values_per_column(pd.DataFrame(m.copy(), columns=names))
+            want = rdf.impute(pd.DataFrame(m.copy(), columns=names)).to_numpy(np.float64)
+            want0 = rdf.impute_dataframe_zero(pd.DataFrame(m.copy(), columns=names)).to_numpy(np.float64)
+        st = oi.range_values(m)
+        assert np.array_equal(st[0], [cmin[c] for c in names])
+        assert np.array_equal(st[1], [cmax[c] for c in names])
+        assert np.array_equal(st[2], [float(cmed[c]) for c in names])
+        assert np.array_equal(oi.impute(m), want)
+        assert np.array_equal(oi.impute_zero(m), want0)

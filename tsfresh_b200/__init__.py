@@ -1,7 +1,11 @@
 """tsfresh_b200 -- B200-native implementation of tsfresh's feature-extraction hot path.
 
-Public surface = the reference's for this path: `extract_features` and the FC-parameter presets."""
+Public surface = the reference's for this path: `extract_features`, the FC-parameter presets and the
+imputation helpers that `extract_features(impute_function=...)` takes."""
 from .extraction import extract_features  # noqa: F401
+from .dataframe_functions import (get_range_values_per_column, impute, impute_dataframe_range,  # noqa: F401
+                                  impute_dataframe_zero)
 from .settings import ComprehensiveFCParameters, EfficientFCParameters, MinimalFCParameters  # noqa: F401
 
-__all__ = ["extract_features", "ComprehensiveFCParameters", "EfficientFCParameters", "MinimalFCParameters"]
+__all__ = ["extract_features", "impute", "impute_dataframe_zero", "impute_dataframe_range",
+           "get_range_values_per_column", "ComprehensiveFCParameters", "EfficientFCParameters", "MinimalFCParameters"]

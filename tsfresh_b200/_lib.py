@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(HERE, "libtsfx.so")
 
 FLAG_DEVICE_PTRS = 1
 FLAG_TIMING = 2
+FLAG_IMPUTE = 8
+FLAG_ALL_MEDIANS = 16
+IMPUTE_RANGE, IMPUTE_ZERO, IMPUTE_GIVEN, IMPUTE_STATS = 0, 1, 2, 3
 
 _ERR = {-1: ValueError, -2: RuntimeError, -3: NotImplementedError, -4: ValueError, -5: MemoryError, -6: ValueError}
 
@@ -22,7 +25,7 @@ _lock = threading.Lock()
 EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync", "tsfx_version",
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
-           "tsfx_last_launch_count"]
+           "tsfx_last_launch_count", "tsfx_impute"]
 
 
 def load():
@@ -53,6 +56,7 @@ def load():
         lib.tsfx_roll_windows.restype = i64
         lib.tsfx_get_timings.argtypes = [vp, vp, vp, i32]
         lib.tsfx_last_launch_count.argtypes = [vp]
+        lib.tsfx_impute.argtypes = [vp, vp, i64, i32, i32, vp, u32]
         _lib = lib
         return lib
 
@@ -105,6 +109,27 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.tsfx_last_launch_count(self.h))
+
+    def impute(self, matrix, mode=IMPUTE_RANGE, col_stats=None, all_medians=False):
+        """tsfx_impute on a host matrix (C-contiguous float64 [rows x cols]), in place.  Returns the
+        [3 x cols] array min | max | median (None for IMPUTE_ZERO)."""
+        if not (isinstance(matrix, np.ndarray) and matrix.dtype == np.float64 and matrix.flags.c_contiguous
+                and matrix.ndim == 2):
+            raise ValueError("impute needs a C-contiguous float64 2-d array")
+        rows, cols = matrix.shape
+        stats = None
+        if mode != IMPUTE_ZERO:
+            stats = np.full((3, cols), np.nan) if col_stats is None else np.ascontiguousarray(col_stats, dtype=np.float64)
+            if stats.shape != (3, cols):
+                raise ValueError("col_stats must have shape (3, n_cols)")
+        rc = self.lib.tsfx_impute(self.h, _ptr(matrix), rows, cols, mode, _ptr(stats),
+                                  FLAG_ALL_MEDIANS if all_medians else 0)
+        self.check(rc, "tsfx_impute")
+        return stats
+
+    def impute_device(self, matrix_ptr, rows, cols, mode=IMPUTE_RANGE):
+        rc = self.lib.tsfx_impute(self.h, ctypes.c_void_p(matrix_ptr), rows, cols, mode, None, FLAG_DEVICE_PTRS)
+        self.check(rc, "tsfx_impute")
 
 
 class DevicePlan:

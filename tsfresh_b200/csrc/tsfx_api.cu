@@ -11,6 +11,7 @@
 #include "tsfx_common.cuh"
 #include "tsfx_kernels.h"
 #include "tsfx_csr.h"
+#include "tsfx_impute.h"
 
 using namespace tsfx;
 
@@ -72,6 +73,7 @@ struct tsfx_ctx {
     float ms[G_EVENTS];
     int launches = 0;
     CsrWorkspace csr;
+    ImputeWorkspace imp;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host path
     cudaStream_t s_side[3] = {nullptr, nullptr, nullptr};   // optional side streams so kernel groups can overlap
@@ -201,6 +203,7 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release(); ctx->stage.release();
     ctx->csr.release();
+    ctx->imp.release();
     if (ctx->d_dec) cudaFree(ctx->d_dec);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     for (int g = 0; g < G_EVENTS; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
@@ -508,6 +511,8 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
     return TSFX_OK;
 }
 
+static int impute_after_extract(tsfx_ctx* ctx, double* d_out, int64_t rows, int cols);
+
 static int check_args(tsfx_ctx* ctx, const tsfx_plan* plan, const void* values, const void* out, int64_t n_series) {
     if (!ctx) return TSFX_E_INVALID;
     if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
@@ -532,7 +537,9 @@ extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const floa
         R.values = values; R.begin = begin; R.len = len;
         int rc2 = csr_max_len(ctx->csr, len, n_series, ctx->stream, &max_len);
         if (rc2) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
-        return run_groups(ctx, plan, R, max_len, out, flags);
+        rc = run_groups(ctx, plan, R, max_len, out, flags);
+        if (!rc && (flags & TSFX_FLAG_IMPUTE)) rc = impute_after_extract(ctx, out, n_series, plan->ncols);
+        return rc;
     }
     for (int64_t s = 0; s < n_series; ++s) {
         if (len[s] < 1 || begin[s] < 0 || begin[s] + len[s] > n_values)
@@ -550,6 +557,7 @@ extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const floa
     R.values = (const float*)ctx->values.p; R.begin = (const int64_t*)ctx->begin.p; R.len = (const int32_t*)ctx->len.p;
     rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
     if (rc) return rc;
+    if (flags & TSFX_FLAG_IMPUTE) { rc = impute_after_extract(ctx, (double*)ctx->out.p, n_series, plan->ncols); if (rc) return rc; }
     CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TSFX_OK;
@@ -566,7 +574,9 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
     R.begin = nullptr; R.len = nullptr; R.dense_len = len; R.n_series = n_series;
     if (flags & TSFX_FLAG_DEVICE_PTRS) {
         R.values = values;
-        return run_groups(ctx, plan, R, len, out, flags);
+        rc = run_groups(ctx, plan, R, len, out, flags);
+        if (!rc && (flags & TSFX_FLAG_IMPUTE)) rc = impute_after_extract(ctx, out, n_series, plan->ncols);
+        return rc;
     }
     // host path: pipelined over row blocks -- the H2D copy of block b+1 and the D2H copy of block b-1 run on
     // their own streams while the kernels of block b execute (pinned host buffers make the copies truly async)
@@ -590,13 +600,62 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
         R.n_series = cnt;
         rc = run_groups(ctx, plan, R, len, dout + (size_t)lo * ncols, flags);
         if (rc) return rc;
+        if (flags & TSFX_FLAG_IMPUTE) continue;         // column statistics need every row: one copy at the end
         CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0));
         CK(cudaMemcpyAsync(out + (size_t)lo * ncols, dout + (size_t)lo * ncols, (size_t)cnt * ncols * sizeof(double),
                            cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    if (flags & TSFX_FLAG_IMPUTE) {
+        rc = impute_after_extract(ctx, dout, n_series, plan->ncols);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+// impute the device matrix of the extract call that just ran (TSFX_FLAG_IMPUTE)
+static int impute_after_extract(tsfx_ctx* ctx, double* d_out, int64_t rows, int cols) {
+    int n = 0;
+    cudaError_t e = impute_device(ctx->imp, d_out, rows, cols, TSFX_IMPUTE_RANGE, false, nullptr, ctx->sm_count, ctx->stream, &n);
+    if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("impute: ") + cudaGetErrorString(e));
+    ctx->launches += n;
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_impute(tsfx_ctx* ctx, double* matrix, int64_t n_rows, int32_t n_cols, int32_t mode, double* col_stats,
+                           uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (n_rows < 0 || n_cols < 0 || mode < TSFX_IMPUTE_RANGE || mode > TSFX_IMPUTE_STATS)
+        return fail(ctx, TSFX_E_INVALID, "tsfx_impute: bad arguments");
+    if (n_rows == 0 || n_cols == 0) return TSFX_OK;
+    if (!matrix) return fail(ctx, TSFX_E_INVALID, "tsfx_impute: NULL matrix");
+    if ((mode == TSFX_IMPUTE_GIVEN || mode == TSFX_IMPUTE_STATS) && !col_stats)
+        return fail(ctx, TSFX_E_INVALID, "tsfx_impute: col_stats is required for this mode");
+    if (mode == TSFX_IMPUTE_GIVEN)
+        for (int64_t i = 0; i < (int64_t)3 * n_cols; ++i)
+            if (!std::isfinite(col_stats[i]))       // dataframe_functions.py:147-156 raises ValueError
+                return fail(ctx, TSFX_E_INVALID, "tsfx_impute: non-finite replacement value");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n_rows * n_cols * sizeof(double);
+    double* d_m = matrix;
+    const bool host = !(flags & TSFX_FLAG_DEVICE_PTRS);
+    if (host) {
+        CK(ctx->out.reserve(bytes));
+        d_m = (double*)ctx->out.p;
+        CK(cudaMemcpyAsync(d_m, matrix, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int n = 0;
+    cudaError_t e = impute_device(ctx->imp, d_m, n_rows, n_cols, mode, (flags & TSFX_FLAG_ALL_MEDIANS) != 0 || mode == TSFX_IMPUTE_STATS,
+                                  col_stats, ctx->sm_count, ctx->stream, &n);
+    if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("impute: ") + cudaGetErrorString(e));
+    ctx->launches = n;
+    if (host) {
+        if (mode != TSFX_IMPUTE_STATS) CK(cudaMemcpyAsync(matrix, d_m, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return TSFX_OK;
 }
 
@@ -680,6 +739,7 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
     R.values = ctx->csr.d_values; R.begin = ctx->csr.d_begin; R.len = ctx->csr.d_len; R.dense_len = 0; R.n_series = ns;
     rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
     if (rc) return rc;
+    if (flags & TSFX_FLAG_IMPUTE) { rc = impute_after_extract(ctx, (double*)ctx->out.p, ns, plan->ncols); if (rc) return rc; }
     if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

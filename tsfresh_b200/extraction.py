@@ -172,6 +172,10 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
 
     frames, id_dtype = _frames(timeseries_container, column_id, column_kind, column_value, column_sort)
     ctx = get_context(device)
+    # impute_function=tsfresh_b200.impute: the feature matrix is imputed on the device before it is copied back
+    from . import dataframe_functions as _dff
+    device_impute = impute_function is _dff.impute
+    extract_flags = _lib.FLAG_IMPUTE if (device_impute and len(frames) == 1 and pivot) else 0
     codes, decoder = _encode_ids([f[1] for f in frames])
 
     blocks = []           # (column names, ids (codes), matrix)
@@ -192,7 +196,7 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             continue
         dp = _device_plan(ctx, plan)
         v32 = values.to_numpy().astype(np.float32, copy=False)
-        uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32)
+        uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags)
         blocks.append((names, uid, mat))
 
     # ---- assemble (PartitionedTsData.pivot, data.py:86-121): union of ids, sorted, id dtype restored
@@ -226,5 +230,11 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
     if not result.index.is_monotonic_increasing:
         result = result.sort_index()
     if impute_function is not None:
-        impute_function(result)
+        if device_impute:
+            if not extract_flags and result.shape[0] and result.shape[1]:      # several kinds: one pass over the union
+                m = np.ascontiguousarray(result.to_numpy(dtype=np.float64))
+                ctx.impute(m, _lib.IMPUTE_RANGE)
+                result = pd.DataFrame(m, index=result.index, columns=result.columns, copy=False)
+        else:
+            impute_function(result)
     return result
