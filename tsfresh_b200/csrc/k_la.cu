@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                             {
                                 // factorise as far as the pivots stay positive (the models are nested)
                                 const int okq = warp_cholesky(G, p, p, lane);
-                                double ssr = *yy, best_ic = 0.0;
-                                bool have = false;
+                                double ssr = *yy;
+                                double ssr_a = 0.0, ssr_b = 0.0;        // residual sum of squares of model q = lane+1 / lane+33
                                 const double dnobs = (double)nobs;
                                 for (int i = 0; i < okq; ++i) {
                                     double z = bvec[i] / G[i * p + i];
@@ -203,14 +203,28 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
                                     for (int r2 = i + 1 + lane; r2 < okq; r2 += 32) bvec[r2] = fma(-G[r2 * p + i], z, bvec[r2]);
                                     __syncwarp();
                                     ssr -= z * z;
-                                    const int q = i + 1;
-                                    if (q >= 2) {
-                                        double llf = -dnobs / 2.0 * log(2.0 * 3.14159265358979323846) -
-                                                     dnobs / 2.0 * log(ssr / dnobs) - dnobs / 2.0;
-                                        double pen = (adf_mode == TSFX_AUTOLAG_AIC) ? 2.0 * (double)q : log(dnobs) * (double)q;
-                                        double ic = -2.0 * llf + pen;
-                                        if (!have || ic < best_ic) { have = true; best_ic = ic; best_q = q; }
+                                    if ((i & 31) == lane) { if (i < 32) ssr_a = ssr; else ssr_b = ssr; }
+                                }
+                                // information criterion of every nested model, one model per lane (the logarithms are
+                                // the expensive part), then the reference's first-minimum scan in model order
+                                double ic_a = 0.0, ic_b = 0.0;
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const int q = c * 32 + lane + 1;
+                                    if (q >= 2 && q <= okq) {
+                                        const double sq = c ? ssr_b : ssr_a;
+                                        const double llf = -dnobs / 2.0 * log(2.0 * 3.14159265358979323846) -
+                                                           dnobs / 2.0 * log(sq / dnobs) - dnobs / 2.0;
+                                        const double pen = (adf_mode == TSFX_AUTOLAG_AIC) ? 2.0 * (double)q : log(dnobs) * (double)q;
+                                        const double ic = -2.0 * llf + pen;
+                                        if (c) ic_b = ic; else ic_a = ic;
                                     }
+                                }
+                                double best_ic = 0.0;
+                                bool have = false;
+                                for (int q = 2; q <= okq; ++q) {
+                                    const double ic = __shfl_sync(FULL, (q > 32) ? ic_b : ic_a, (q - 1) & 31);
+                                    if (!have || ic < best_ic) { have = true; best_ic = ic; best_q = q; }
                                 }
                             }
                             best_q = __shfl_sync(FULL, best_q, 0);
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(WPC * 32) k_la(LaArgs A, int pmax) {
 cudaError_t launch_la(const LaArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     LaArgs A = A0;
     A.npad = (max_len + 3) & ~3;
+    if (adf_maxlag(max_len) + 2 > 64) return cudaErrorInvalidConfiguration;     // autolag keeps one model per lane, two rounds
     int pmax = std::max(adf_maxlag(max_len) + 2, A.nscr + 1);   // nscr carries the plan's largest AR order k
     pmax = (pmax + 1) & ~1;
     size_t per = (size_t)A.npad * 16 + (size_t)pmax * pmax * 16 + (size_t)pmax * 24 + 64 + (size_t)A.npad * 4;

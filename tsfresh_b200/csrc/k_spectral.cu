@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
         for (int j = A.nfft; j < A.nd; ++j) {
             const Desc d = A.descs[j];
             double r = dnan();
+            bool stored = false;
             switch (d.calc) {
                 case TSFX_FFT_AGGREGATED: {
                     double m1 = am1 / am0, m2 = am2 / am0, m3 = am3 / am0, m4 = am4 / am0;
@@ -267,22 +268,40 @@ __global__ void __launch_bounds__(WPC * 32) k_spectral(SpectralArgs A, int nwtab
                     break;
                 }
                 case TSFX_CWT_COEFFICIENTS: {
-                    const int c = d.i0;
-                    if (n <= c) { r = dnan(); break; }
-                    const double* D = A.tables + A.table_off[d.i1];
-                    const int dl = (int)(A.table_off[d.i1 + 1] - A.table_off[d.i1]);
-                    const int top = c + A.table_half[d.i1];            // D index for k = 0
-                    int k0 = top - (dl - 1);
-                    if (k0 < 0) k0 = 0;
-                    int k1 = top < n - 1 ? top : n - 1;
-                    double a = 0.0;
-                    for (int k = k0 + lane; k <= k1; k += 32) a = fma((double)xs[k], __ldg(D + (top - k)), a);
-                    r = wsum(a);
+                    // the whole run of cwt_coefficients descriptors (sorted by width, descriptor j writes column j):
+                    // one coefficient per lane, each lane walks the taps of its wavelet row serially -- no warp
+                    // sum and one trip through this loop instead of one per column
+                    int run = 0;
+                    for (;;) {
+                        const int jj = j + run + lane;
+                        const unsigned same = __ballot_sync(FULL, jj < A.nd && A.descs[jj].calc == TSFX_CWT_COEFFICIENTS);
+                        if (same == FULL) { run += 32; continue; }
+                        run += __ffs(~same) - 1;
+                        break;
+                    }
+                    for (int t = lane; t < run; t += 32) {
+                        const Desc e = A.descs[j + t];
+                        const int c = e.i0;
+                        double a = dnan();
+                        if (n > c) {
+                            const double* D = A.tables + A.table_off[e.i1];
+                            const int dl = (int)(A.table_off[e.i1 + 1] - A.table_off[e.i1]);
+                            const int top = c + A.table_half[e.i1];        // D index for k = 0
+                            int k0 = top - (dl - 1);
+                            if (k0 < 0) k0 = 0;
+                            const int k1 = top < n - 1 ? top : n - 1;
+                            a = 0.0;
+                            for (int k = k0; k <= k1; ++k) a = fma((double)xs[k], __ldg(D + (top - k)), a);
+                        }
+                        orow[j + t] = a;
+                    }
+                    stored = true;
+                    j += run - 1;
                     break;
                 }
                 default: break;
             }
-            if (lane == 0) orow[d.col] = r;
+            if (!stored && lane == 0) orow[d.col] = r;
         }
         __syncwarp();
     }

@@ -4,9 +4,10 @@
 // (finite max / min / median per column; a column without any finite value -> 0 for all three) followed by
 // impute_dataframe_range :104-167 (+inf -> max, -inf -> min, NaN -> median), and impute_dataframe_zero :81-101.
 //
-// The matrix is the row-major [rows x cols] float64 block the extraction kernels write.  Two HBM-bound sweeps
-// (statistics, replacement) with warps reading 32 consecutive columns of a row (256 B), plus one radix sort per
-// column that actually needs a median (it contains a NaN) or for every column when the caller asks for the medians.
+// The matrix is the row-major [rows x cols] float64 block the extraction kernels write.  One HBM-bound statistics
+// sweep (warps read 32 consecutive columns of a row, 256 B, four rows in flight per thread), one radix sort per
+// column that actually needs a median (it contains a NaN; every column when the caller asks for the medians), and a
+// replacement sweep that skips every (row slice, column tile) the statistics found clean.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -21,6 +22,7 @@ namespace {
 
 constexpr int TILE_C = 32;      // columns per block (one warp reads one 256-byte row segment)
 constexpr int TILE_R = 8;       // row lanes per block
+constexpr int UNR = 4;          // rows per thread and trip (memory-level parallelism)
 
 struct ColPartial { double vmin, vmax; long long finite, nan; };
 
@@ -33,10 +35,19 @@ __global__ void __launch_bounds__(TILE_C * TILE_R) k_col_stats(const double* __r
     ColPartial p;
     p.vmin = INFINITY; p.vmax = -INFINITY; p.finite = 0; p.nan = 0;
     if (c < cols) {
-        for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += TILE_R) {
-            const double v = m[(size_t)r * cols + c];
-            if (isfinite(v)) { p.vmin = fmin(p.vmin, v); p.vmax = fmax(p.vmax, v); ++p.finite; }
-            else if (v != v) ++p.nan;
+        for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += UNR * TILE_R) {       // UNR independent loads in flight
+            double v[UNR];
+#pragma unroll
+            for (int q = 0; q < UNR; ++q) {
+                const int64_t rr = r + (int64_t)q * TILE_R;
+                v[q] = rr < r_hi ? m[(size_t)rr * cols + c] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < UNR; ++q) {
+                if (r + (int64_t)q * TILE_R >= r_hi) break;
+                if (isfinite(v[q])) { p.vmin = fmin(p.vmin, v[q]); p.vmax = fmax(p.vmax, v[q]); ++p.finite; }
+                else if (v[q] != v[q]) ++p.nan;
+            }
         }
     }
     sh[threadIdx.y][threadIdx.x] = p;
@@ -82,20 +93,32 @@ __global__ void k_pick_median(const double* __restrict__ sorted, long long finit
     *dst = (lo == hi) ? lo : (lo + hi) / 2.0;
 }
 
-// mode 0: +inf -> max, -inf -> min, NaN -> median;  mode 1: every non-finite value -> 0
+// zero_mode 0: +inf -> max, -inf -> min, NaN -> median;  zero_mode 1: every non-finite value -> 0.
+// With the partials of the statistics sweep a block first asks whether its (row slice, column tile) holds any
+// non-finite value at all and leaves otherwise: on a typical feature matrix the replacement sweep touches a few tiles.
 __global__ void __launch_bounds__(TILE_C * TILE_R) k_impute_apply(double* __restrict__ m, int64_t rows, int cols,
                                                                  int64_t rows_per_slice, const double* __restrict__ stats,
-                                                                 int zero_mode) {
+                                                                 const ColPartial* __restrict__ part, int zero_mode) {
     const int c = blockIdx.x * TILE_C + threadIdx.x;
-    if (c >= cols) return;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_slice;
     const int64_t r_hi = r_lo + rows_per_slice < rows ? r_lo + rows_per_slice : rows;
+    if (part) {
+        const int dirty = (c < cols) && (part[(size_t)blockIdx.y * cols + c].finite != (long long)(r_hi - r_lo));
+        if (!__syncthreads_or(dirty)) return;
+    }
+    if (c >= cols) return;
     double vmin = 0.0, vmax = 0.0, vmed = 0.0;
     if (!zero_mode) { vmin = stats[c]; vmax = stats[cols + c]; vmed = stats[2 * cols + c]; }
-    for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += TILE_R) {
-        const size_t at = (size_t)r * cols + c;
-        const double v = m[at];
-        if (!isfinite(v)) m[at] = (v != v) ? vmed : (v > 0.0 ? vmax : vmin);
+    for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += UNR * TILE_R) {
+        double v[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int64_t rr = r + (int64_t)q * TILE_R;
+            v[q] = rr < r_hi ? m[(size_t)rr * cols + c] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q)
+            if (!isfinite(v[q])) m[(size_t)(r + (int64_t)q * TILE_R) * cols + c] = (v[q] != v[q]) ? vmed : (v[q] > 0.0 ? vmax : vmin);
     }
 }
 
@@ -131,13 +154,13 @@ cudaError_t impute_device(ImputeWorkspace& W, double* d_m, int64_t rows, int col
     double* d_stats = (double*)W.bufs[1];
 
     if (mode == TSFX_IMPUTE_ZERO) {
-        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, 1);
+        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, nullptr, 1);
         if (launches) *launches = 1;
         return cudaGetLastError();
     }
     if (mode == TSFX_IMPUTE_GIVEN) {           // caller-provided replacement values (impute_dataframe_range)
         ICK(cudaMemcpyAsync(d_stats, h_stats, (size_t)3 * cols * sizeof(double), cudaMemcpyHostToDevice, st));
-        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, 0);
+        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, nullptr, 0);
         if (launches) *launches = 1;
         return cudaGetLastError();
     }
@@ -175,7 +198,7 @@ cudaError_t impute_device(ImputeWorkspace& W, double* d_m, int64_t rows, int col
         n_launch += 4;                                              // gather + radix sort passes (counted as 2) + pick
     }
     if (mode == TSFX_IMPUTE_RANGE) {
-        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, 0);
+        k_impute_apply<<<grid, block, 0, st>>>(d_m, rows, cols, rows_per_slice, d_stats, (const ColPartial*)W.bufs[0], 0);
         ++n_launch;
     }
     if (h_stats) {
