@@ -22,9 +22,20 @@ namespace {
 
 constexpr int TILE_C = 32;      // columns per block (one warp reads one 256-byte row segment)
 constexpr int TILE_R = 8;       // row lanes per block
-constexpr int UNR = 4;          // rows per thread and trip (memory-level parallelism)
+constexpr int UNR = 8;          // rows per thread and trip (memory-level parallelism)
 
 struct ColPartial { double vmin, vmax; long long finite, nan; };
+
+// finite <=> exponent field != all ones (integer test on the high word: cheaper than isfinite() on FP64)
+__device__ __forceinline__ bool finite_bits(double v) { return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000; }
+
+__device__ __forceinline__ void stat_update(double v, double& vmin, double& vmax, int& fin, int& nan) {
+    if (finite_bits(v)) {
+        vmin = v < vmin ? v : vmin;
+        vmax = v > vmax ? v : vmax;
+        ++fin;
+    } else if (v != v) ++nan;
+}
 
 __global__ void __launch_bounds__(TILE_C * TILE_R) k_col_stats(const double* __restrict__ m, int64_t rows, int cols,
                                                               int64_t rows_per_slice, ColPartial* __restrict__ part) {
@@ -32,24 +43,26 @@ __global__ void __launch_bounds__(TILE_C * TILE_R) k_col_stats(const double* __r
     const int c = blockIdx.x * TILE_C + threadIdx.x;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_slice;
     const int64_t r_hi = r_lo + rows_per_slice < rows ? r_lo + rows_per_slice : rows;
-    ColPartial p;
-    p.vmin = INFINITY; p.vmax = -INFINITY; p.finite = 0; p.nan = 0;
+    double vmin = INFINITY, vmax = -INFINITY;
+    int fin = 0, nan = 0;                                   // a thread sees rows_per_slice / TILE_R rows: int is plenty
     if (c < cols) {
-        for (int64_t r = r_lo + threadIdx.y; r < r_hi; r += UNR * TILE_R) {       // UNR independent loads in flight
+        const int64_t first = r_lo + threadIdx.y;
+        const int64_t mine = first < r_hi ? (r_hi - first + TILE_R - 1) / TILE_R : 0;     // rows of this thread
+        const size_t step = (size_t)TILE_R * cols;
+        const double* ptr = m + (size_t)first * cols + c;
+        int64_t k = 0;
+        for (; k + UNR <= mine; k += UNR) {                // UNR independent loads in flight
             double v[UNR];
 #pragma unroll
-            for (int q = 0; q < UNR; ++q) {
-                const int64_t rr = r + (int64_t)q * TILE_R;
-                v[q] = rr < r_hi ? m[(size_t)rr * cols + c] : 0.0;
-            }
+            for (int q = 0; q < UNR; ++q) v[q] = ptr[(size_t)q * step];
+            ptr += (size_t)UNR * step;
 #pragma unroll
-            for (int q = 0; q < UNR; ++q) {
-                if (r + (int64_t)q * TILE_R >= r_hi) break;
-                if (isfinite(v[q])) { p.vmin = fmin(p.vmin, v[q]); p.vmax = fmax(p.vmax, v[q]); ++p.finite; }
-                else if (v[q] != v[q]) ++p.nan;
-            }
+            for (int q = 0; q < UNR; ++q) stat_update(v[q], vmin, vmax, fin, nan);
         }
+        for (; k < mine; ++k) { stat_update(*ptr, vmin, vmax, fin, nan); ptr += step; }
     }
+    ColPartial p;
+    p.vmin = vmin; p.vmax = vmax; p.finite = fin; p.nan = nan;
     sh[threadIdx.y][threadIdx.x] = p;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
