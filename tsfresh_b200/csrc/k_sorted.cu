@@ -208,7 +208,7 @@ __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt,
 }
 
 template <int WPC, bool GS>
-__global__ void __launch_bounds__(WPC * 32) k_sorted(SortedArgs A) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_sorted(SortedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
