@@ -204,9 +204,13 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
-        # keep stdout to the single JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the single JSON line: NCCL prints its version banner with printf on fd 1 when the first
+        # communicator is created, so fd 1 points at stderr until the result line is written
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     S, L = args.series, args.len
@@ -407,8 +411,19 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cb,
         }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            try:
+                import ctypes
+                ctypes.CDLL(None).fflush(None)       # whatever C code buffered for "stdout" leaves through stderr too
+            except Exception:
+                pass
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        if saved_stdout is not None and rank != 0:
+            os.dup2(saved_stdout, 1)
         dist.destroy_process_group()
 
 
