@@ -201,10 +201,12 @@ int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sort_keys, int
                    const float* values, int64_t n_rows, int64_t* out_ids, int64_t* out_begin,
                    int32_t* out_len, float* sorted_values, int64_t out_capacity, int64_t* n_series_out);
 
-/* roll_time_series as views: for every series s of the input CSR and every window end t
- * (dataframe_functions.py:340-373, positive rolling_direction), emits win_begin/win_len over the SAME
- * values buffer plus (parent, t_end_index).  Returns the number of windows (or a negative error);
- * pass NULL outputs to only count. */
+/* roll_time_series as views: for every series s of the input CSR and every shift t of
+ * dataframe_functions.py:340-373, 548-562 (positive rolling_direction: windows END at row t-1; negative: windows
+ * START at row t-1) emits win_begin/win_len over the SAME values buffer plus (parent, index of the row whose sort
+ * value names the window: its last row for positive, its first row for negative direction).  max_timeshift is the
+ * reference's value (window length - 1; pass a number >= the longest series for "None").  Returns the number of
+ * windows (or a negative error); pass NULL outputs to only count. */
 int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, int64_t n_series,
                           int32_t rolling_direction, int32_t max_timeshift, int32_t min_timeshift,
                           int64_t* win_begin, int32_t* win_len, int64_t* win_parent,

@@ -132,6 +132,29 @@ def test_rolled_windows_as_views_match_oracle_on_materialised_windows():
     assert not bad, bad[:20]
 
 
+def test_extract_features_on_rolled_views():
+    """extract_features(roll_time_series(df, ...)): the two reference calls, with windows as views; equals the oracle on
+    the materialised windows, index = (id, time of the id row), both rolling directions, two value columns."""
+    from tsfresh_b200 import impute, roll_time_series
+    from oracle import impute as oi
+    series = list(synthetic_series(31, 3, 90)) + [synthetic_series(32, 1, 40)[0]]
+    df = long_frame(series, ids=[7, 3, 11, 5], shuffle_seed=4)
+    df["other"] = (df["value"] * 2 + 1).astype(np.float32)
+    settings = EfficientFCParameters()
+    plan = Plan(settings)
+    for rd, mx, mn in ((16, 31, 31), (-16, 31, 31), (25, 40, 9)):
+        rolled = roll_time_series(df, column_id="id", column_sort="time", rolling_direction=rd, max_timeshift=mx, min_timeshift=mn)
+        X = extract_features(rolled, default_fc_parameters=settings)
+        assert list(X.index) == rolled.ids and len(X) == len(rolled) > 0
+        assert list(X.columns) == ["value__" + s for s in plan.suffixes] + ["other__" + s for s in plan.suffixes]
+        for kind, lo in (("value", 0), ("other", plan.n_cols)):
+            windows = [rolled.values[kind][b:b + n].astype(np.float64) for b, n in zip(rolled.begin, rolled.length)]
+            bad = compare(X.to_numpy()[:, lo:lo + plan.n_cols], oracle_rows(windows, settings), plan.suffixes)
+            assert not bad, (rd, kind, bad[:10])
+    Xi = extract_features(rolled, default_fc_parameters=settings, impute_function=impute)
+    assert np.array_equal(Xi.to_numpy(), oi.impute(X.to_numpy()))
+
+
 def test_distributor_plugin_map_reduce():
     """The reference's plugin seam (utilities/distribution.py:74-104): extract_features hands the distributor
     `data` (an iterable of (id, kind, pd.Series)) and `function_kwargs`; B200Distributor must return the triples

@@ -80,6 +80,55 @@ def test_roll_windows_match_reference_roll_time_series():
     assert len(wb) == 242 and set(wl.tolist()) == {256} and we.max() == 4095
 
 
+def test_roll_windows_both_directions_match_reference_cases():
+    """tests/golden/roll_cases.npz (oracle/make_golden_roll.py, unmodified reference): positive and negative
+    rolling_direction, with / without min_timeshift, max_timeshift beyond the longest series."""
+    z = np.load(os.path.join(G, "roll_cases.npz"))
+    lens = z["lens"].astype(np.int32)
+    begin = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    for k, (rd, mx, mn) in enumerate(z["cases"].tolist()):
+        wb, wl, wp, we = _lib.roll_windows(begin, lens, rd, mx, mn)
+        got = sorted((int(p), int(e), int(b - begin[p]), int(l)) for b, l, p, e in zip(wb, wl, wp, we))
+        assert got == [tuple(r) for r in z["case%d" % k].tolist()], (rd, mx, mn)
+    with pytest.raises(ValueError):
+        _lib.roll_windows(begin, lens, 0, 3, 0)
+
+
+def test_roll_time_series_views_ids_and_errors():
+    """tsfresh_b200.roll_time_series: window ids / extents on the golden cases + the reference's validation errors
+    (dataframe_functions.py:455-515)."""
+    import pandas as pd
+    from tsfresh_b200 import roll_time_series
+    z = np.load(os.path.join(G, "roll_cases.npz"))
+    lens = z["lens"].tolist()
+    df = pd.DataFrame({"id": np.concatenate([np.full(n, i) for i, n in enumerate(lens)]),
+                       "time": np.concatenate([np.arange(n) for n in lens]),
+                       "value": np.arange(sum(lens), dtype=np.float32)})
+    begin = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    for k, (rd, mx, mn) in enumerate(z["cases"].tolist()):
+        r = roll_time_series(df.sample(frac=1.0, random_state=k), column_id="id", column_sort="time",
+                             rolling_direction=rd, max_timeshift=mx, min_timeshift=mn)
+        got = sorted((i[0], i[1], int(b - begin[i[0]]), int(n)) for i, b, n in zip(r.ids, r.begin, r.length))
+        assert got == [tuple(x) for x in z["case%d" % k].tolist()]
+        assert r.ids == sorted(r.ids) and r.kinds == ["value"]
+        assert np.array_equal(r.values["value"], df["value"].to_numpy())        # series order restored
+    with pytest.raises(ValueError):
+        roll_time_series(df, column_id="id", rolling_direction=0)
+    with pytest.raises(ValueError):
+        roll_time_series(df, column_id="id", max_timeshift=0)
+    with pytest.raises(ValueError):
+        roll_time_series(df, column_id="id", min_timeshift=-1)
+    with pytest.raises(ValueError):
+        roll_time_series(df.iloc[:1], column_id="id")
+    with pytest.raises(ValueError):
+        roll_time_series(df, column_id=None)
+    with pytest.raises(AttributeError):
+        roll_time_series(df, column_id="nope")
+    with pytest.raises(ValueError):
+        roll_time_series({"a": df}, column_id="id", column_kind="k")
+    assert set(roll_time_series({"a": df, "b": df}, column_id="id", column_sort="time").keys()) == {"a", "b"}
+
+
 def _gloo_worker(rank, world, port, n_rows, q):
     import torch
     import torch.distributed as dist

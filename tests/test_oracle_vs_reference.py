@@ -83,3 +83,36 @@ def test_oracle_impute_matches_reference():
         assert np.array_equal(st[2], [float(cmed[c]) for c in names])
         assert np.array_equal(oi.impute(m), want)
         assert np.array_equal(oi.impute_zero(m), want0)
+
+
+def test_roll_time_series_views_reproduce_reference_frame():
+    """tsfresh_b200.roll_time_series(...).to_frame() == the reference's materialised rolled frame (ids, row order,
+    values) for both directions, shuffled input and a missing sort column."""
+    ref_shim.load()
+    from tsfresh.utilities.dataframe_functions import roll_time_series as ref_roll
+    from tsfresh_b200 import roll_time_series
+    rng = np.random.default_rng(3)
+    lens = [20, 9, 31, 1, 2]
+    df = pd.DataFrame({"id": np.concatenate([np.full(n, i * 10) for i, n in enumerate(lens)]),
+                       "time": np.concatenate([np.arange(n) * 2 + 5 for n in lens]),
+                       "a": rng.standard_normal(sum(lens)).astype(np.float32),
+                       "b": rng.standard_normal(sum(lens)).astype(np.float32)})
+    for shuffle in (False, True):
+        d = df.sample(frac=1.0, random_state=1).reset_index(drop=True) if shuffle else df
+        for rd, mx, mn in [(-1, 7, 0), (-3, 7, 7), (3, 7, 0), (1, None, 3), (2, 4, 4)]:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = ref_roll(d.copy(), column_id="id", column_sort="time", rolling_direction=rd, max_timeshift=mx,
+                                min_timeshift=mn, n_jobs=0, disable_progressbar=True).reset_index(drop=True)
+            got = roll_time_series(d, column_id="id", column_sort="time", rolling_direction=rd, max_timeshift=mx,
+                                   min_timeshift=mn).to_frame()
+            assert list(want["id"]) == list(got["id"]), (shuffle, rd, mx, mn)
+            assert np.array_equal(want["time"], got["time"])
+            for c in "ab":
+                assert np.array_equal(want[c].to_numpy(np.float32), got[c])
+    d = df.drop(columns=["time"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ref_roll(d.copy(), column_id="id", rolling_direction=2, max_timeshift=5, n_jobs=0, disable_progressbar=True)
+    got = roll_time_series(d, column_id="id", rolling_direction=2, max_timeshift=5).to_frame()
+    assert list(want["id"]) == list(got["id"]) and np.array_equal(want["sort"].to_numpy(), got["sort"].to_numpy())

@@ -751,24 +751,34 @@ extern "C" int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, i
                                      int32_t rolling_direction, int32_t max_timeshift, int32_t min_timeshift,
                                      int64_t* win_begin, int32_t* win_len, int64_t* win_parent,
                                      int32_t* win_end_index, int64_t capacity) {
-    // dataframe_functions.py:340-373, 548-562 with rolling_direction > 0: the shifts are
+    // dataframe_functions.py:340-373, 548-562.  rolling_direction > 0: the shifts are
     // reversed(range(Lmax, 0, -rolling_direction)) where Lmax is the LONGEST series of the frame (:555-560), so
     // window ends are anchored to Lmax for every series; shift t applies to a series of length L when t <= L,
     // the window is rows [max(t-max_timeshift-1, 0), t), kept when it has at least min_timeshift+1 rows, and
     // its id is (parent id, time of row t-1).
-    if (!begin || !len || n_series < 0 || rolling_direction <= 0 || max_timeshift < 0 || min_timeshift < 0)
+    // rolling_direction < 0 (:351-356, 365-366): shifts range(1, Lmax+1, |rolling_direction|), the window is rows
+    // [t-1, min(t+max_timeshift, L)), same minimum length, id = (parent id, time of row t-1) -- the window's FIRST row.
+    // win_end_index is therefore "the row whose sort value names the window": last row (positive) / first row (negative).
+    if (!begin || !len || n_series < 0 || rolling_direction == 0 || max_timeshift < 0 || min_timeshift < 0)
         return TSFX_E_INVALID;
     int32_t Lmax = 0;
     for (int64_t s = 0; s < n_series; ++s) { if (len[s] < 1) return TSFX_E_INVALID; Lmax = std::max(Lmax, len[s]); }
-    const int32_t first = Lmax > 0 ? Lmax - ((Lmax - 1) / rolling_direction) * rolling_direction : 1;   // smallest shift
+    const int32_t amount = rolling_direction > 0 ? rolling_direction : -rolling_direction;
+    const int32_t first = rolling_direction > 0 ? (Lmax > 0 ? Lmax - ((Lmax - 1) / amount) * amount : 1) : 1;   // smallest shift
     int64_t k = 0;
     for (int64_t s = 0; s < n_series; ++s) {
-        int32_t L = len[s];
-        if (L < 1) return TSFX_E_INVALID;
-        for (int32_t t = first; t <= L; t += rolling_direction) {
-            int32_t lo = t - max_timeshift - 1;
-            if (lo < 0) lo = 0;
-            int32_t wl = t - lo;
+        const int32_t L = len[s];
+        for (int32_t t = first; t <= L; t += amount) {
+            int32_t lo, wl;
+            if (rolling_direction > 0) {
+                lo = t - max_timeshift - 1;
+                if (lo < 0) lo = 0;
+                wl = t - lo;
+            } else {
+                lo = t - 1;
+                const int64_t hi = std::min<int64_t>((int64_t)lo + max_timeshift + 1, L);
+                wl = (int32_t)(hi - lo);
+            }
             if (wl < min_timeshift + 1) continue;
             if (win_begin) {
                 if (k >= capacity) return TSFX_E_INVALID;

@@ -153,6 +153,31 @@ def _encode_ids(id_series_list):
     return codes, uniq
 
 
+def _extract_rolled(rolled, default_fc_parameters, kind_to_fc_parameters, impute_function, show_warnings, device):
+    """extract_features(roll_time_series(...)): every window is a (begin, len) view on the kind's value buffer
+    (tsfresh_b200.rolling); same result frame as the reference gives on its materialised rolled frame."""
+    from . import dataframe_functions as _dff
+    ctx = get_context(device)
+    device_impute = impute_function is _dff.impute
+    blocks, columns = [], []
+    for kind in rolled.kinds:
+        fc = kind_to_fc_parameters[kind] if (kind_to_fc_parameters and kind in kind_to_fc_parameters) else default_fc_parameters
+        plan = Plan(fc)
+        columns += [kind + "__" + s for s in plan.suffixes]
+        if plan.n_cols == 0 or len(rolled) == 0:
+            blocks.append(np.empty((len(rolled), plan.n_cols)))
+            continue
+        dp = _device_plan(ctx, plan)
+        flags = _lib.FLAG_IMPUTE if device_impute else 0          # columns are independent: per-kind impute is exact
+        blocks.append(dp.extract_csr(rolled.values[kind], rolled.begin, rolled.length, flags=flags))
+    data = blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1)
+    index = pd.Index(rolled.ids, tupleize_cols=False)
+    result = pd.DataFrame(data, index=index, columns=columns, copy=False)
+    if impute_function is not None and not device_impute:
+        impute_function(result)
+    return result
+
+
 def extract_features(timeseries_container, default_fc_parameters=None, kind_to_fc_parameters=None, column_id=None,
                      column_sort=None, column_kind=None, column_value=None, chunksize=None, n_jobs=1,
                      show_warnings=False, disable_progressbar=False, impute_function=None, profile=False,
@@ -165,6 +190,10 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
         default_fc_parameters = ComprehensiveFCParameters()
     elif default_fc_parameters is None and kind_to_fc_parameters is not None:
         default_fc_parameters = {}
+    from .rolling import RolledTimeSeries
+    if isinstance(timeseries_container, RolledTimeSeries):
+        return _extract_rolled(timeseries_container, default_fc_parameters, kind_to_fc_parameters, impute_function,
+                               show_warnings, device)
     if distributor is not None:
         from .distributor import is_distributor
         if not is_distributor(distributor):
