@@ -1,8 +1,10 @@
 // k_basic.cu -- kernel group BASIC: moments / extrema / counts / order-dependent streams.
 //
 // One warp per series.  Shared memory per warp: xs[npad] float32 (the series as ingested),
-// xc[npad] float64 (centred copy x - mean), scr[nscr] float64 (scratch: chunk aggregates, histograms),
-// lagS[nlag] float64 (lag products).  Calculators restated (feature_calculators.py line numbers in
+// xc[nxc] float64 (centred copy x - mean with a zero tail for the tiled lag products), scr[nscr] float64
+// (scratch: chunk aggregates, histograms, cumulative masses, peak radii), lagS[nlag] float64 (lag products, pacf),
+// ST[32] (shared statistics read by the lane-parallel finishers), altS[6 nalt] (regression sums per
+// agg_linear_trend key).  Calculators restated (feature_calculators.py line numbers in
 // include/tsfx.h): every "class M" and "class O" row of SURVEY.md section 8a.
 #include "tsfx_common.cuh"
 #include "tsfx_math.cuh"

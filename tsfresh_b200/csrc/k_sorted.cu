@@ -4,7 +4,8 @@
 // max_langevin_fixed_point.
 //
 // One warp per series; one in-shared-memory bitonic sort (float32 keys, +inf padding) shared by all of
-// them.  Shared memory per warp: xs[npad] (time order), srt[npow2] (ascending), scr[nscr] float64.
+// them.  Shared memory per warp: xs[npad] (time order), srt[npow2] (ascending), scr[nscr] float64,
+// cqS[5 ncq] (count / means / variances per change_quantiles corridor).
 #include <algorithm>
 
 #include "tsfx_common.cuh"
