@@ -153,6 +153,23 @@ def test_extract_features_on_rolled_views():
             assert not bad, (rd, kind, bad[:10])
     Xi = extract_features(rolled, default_fc_parameters=settings, impute_function=impute)
     assert np.array_equal(Xi.to_numpy(), oi.impute(X.to_numpy()))
+    # long format with a kind column: kinds of different length, rows = union of the window ids
+    stacked = pd.concat([df[["id", "time", "value"]].assign(kind="a"),
+                         df[df["time"] < 50][["id", "time", "other"]].rename(columns={"other": "value"}).assign(kind="b")],
+                        ignore_index=True)
+    rk = roll_time_series(stacked, column_id="id", column_sort="time", column_kind="kind", rolling_direction=16,
+                          max_timeshift=31, min_timeshift=31)
+    Xk = extract_features(rk, default_fc_parameters=settings)
+    assert list(Xk.columns) == ["a__" + s for s in plan.suffixes] + ["b__" + s for s in plan.suffixes]
+    assert list(Xk.index) == sorted(set(rk.parts["a"].ids) | set(rk.parts["b"].ids))
+    for kind, lo in (("a", 0), ("b", plan.n_cols)):
+        part = rk.parts[kind]
+        windows = [part.values["value"][b:b + n].astype(np.float64) for b, n in zip(part.begin, part.length)]
+        got = Xk.loc[pd.Index(part.ids, tupleize_cols=False)].to_numpy()[:, lo:lo + plan.n_cols]
+        bad = compare(got, oracle_rows(windows, settings), plan.suffixes)
+        assert not bad, (kind, bad[:10])
+    missing = [w for w in Xk.index if w not in set(rk.parts["b"].ids)]
+    assert missing and np.isnan(Xk.loc[pd.Index(missing, tupleize_cols=False)].to_numpy()[:, plan.n_cols:]).all()
 
 
 def test_distributor_plugin_map_reduce():

@@ -129,6 +129,32 @@ def test_roll_time_series_views_ids_and_errors():
     assert set(roll_time_series({"a": df, "b": df}, column_id="id", column_sort="time").keys()) == {"a", "b"}
 
 
+def test_roll_time_series_known_answers_of_the_reference_tests():
+    """Constants of the reference's RollingTestCase (tests/units/utilities/test_dataframe_functions.py:148-740)."""
+    import pandas as pd
+    from tsfresh_b200 import roll_time_series
+    first = pd.DataFrame({"a": [1, 2, 3, 4], "b": [5, 6, 7, 8], "time": range(4), "id": 1})
+    second = pd.DataFrame({"a": [10, 11], "b": [12, 13], "time": range(20, 22), "id": 2})
+    df = pd.concat([first, second], ignore_index=True)
+    f = roll_time_series(df, column_id="id", column_sort="time", rolling_direction=1).to_frame()          # :148-230
+    assert list(f["id"]) == [(1, 0)] + [(1, 1)] * 2 + [(1, 2)] * 3 + [(1, 3)] * 4 + [(2, 20)] + [(2, 21)] * 2
+    assert list(f["a"]) == [1, 1, 2, 1, 2, 3, 1, 2, 3, 4, 10, 10, 11]
+    assert list(f["b"]) == [5, 5, 6, 5, 6, 7, 5, 6, 7, 8, 12, 12, 13]
+    f = roll_time_series(df, column_id="id", column_sort="time", rolling_direction=2).to_frame()          # :578-625
+    assert list(f["id"]) == [(1, 1)] * 2 + [(1, 3)] * 4 + [(2, 21)] * 2
+    assert list(f["a"]) == [1, 2, 1, 2, 3, 4, 10, 11]
+    f = roll_time_series(df, column_id="id", column_sort="time", rolling_direction=-2).to_frame()         # :627-650
+    assert list(f["id"]) == [(1, 0)] * 4 + [(1, 2)] * 2 + [(2, 20)] * 2
+    assert list(f["a"]) == [1, 2, 3, 4, 3, 4, 10, 11] and list(f["b"]) == [5, 6, 7, 8, 7, 8, 12, 13]
+    stacked = pd.concat([df[["time", "id", "a"]].rename(columns={"a": "_value"}),                         # :652-740
+                         df[["time", "id", "b"]].rename(columns={"b": "_value"})], ignore_index=True)
+    stacked["kind"] = ["a"] * 6 + ["b"] * 6
+    f = roll_time_series(stacked, column_id="id", column_sort="time", column_kind="kind", rolling_direction=-1).to_frame()
+    assert list(f["id"]) == ([(1, 0)] * 8 + [(1, 1)] * 6 + [(1, 2)] * 4 + [(1, 3)] * 2 + [(2, 20)] * 4 + [(2, 21)] * 2)
+    assert list(f["kind"]) == ["a", "b"] * 13
+    assert list(f["_value"]) == [1, 5, 2, 6, 3, 7, 4, 8, 2, 6, 3, 7, 4, 8, 3, 7, 4, 8, 4, 8, 10, 12, 11, 13, 11, 13]
+
+
 def _gloo_worker(rank, world, port, n_rows, q):
     import torch
     import torch.distributed as dist

@@ -116,3 +116,49 @@ def test_roll_time_series_views_reproduce_reference_frame():
         want = ref_roll(d.copy(), column_id="id", rolling_direction=2, max_timeshift=5, n_jobs=0, disable_progressbar=True)
     got = roll_time_series(d, column_id="id", rolling_direction=2, max_timeshift=5).to_frame()
     assert list(want["id"]) == list(got["id"]) and np.array_equal(want["sort"].to_numpy(), got["sort"].to_numpy())
+
+
+def test_reference_rolling_test_cases_pass_on_the_view_implementation():
+    """The reference's own RollingTestCase (tests/units/utilities/test_dataframe_functions.py:18-944) run against
+    tsfresh_b200.roll_time_series(...).to_frame(): positive / negative / larger-shift / stacked (kind column) / dict /
+    order / warning / validation cases."""
+    import importlib.util
+    import os
+    import unittest
+    ref_shim.load()
+    from tsfresh.utilities import dataframe_functions as rdf
+    from tsfresh_b200 import roll_time_series as mine
+
+    def adapter(df_or_dict, column_id, column_sort=None, column_kind=None, rolling_direction=1, max_timeshift=None,
+                min_timeshift=0, **kw):
+        r = mine(df_or_dict, column_id, column_sort=column_sort, column_kind=column_kind,
+                 rolling_direction=rolling_direction, max_timeshift=max_timeshift, min_timeshift=min_timeshift,
+                 show_warnings=True)
+        return {k: v.to_frame() for k, v in r.items()} if isinstance(r, dict) else r.to_frame()
+
+    import sys
+    original = rdf.roll_time_series
+    rdf.roll_time_series = adapter
+    # the reference test module does `from tests.fixtures import warning_free`; `tests` is THIS repo's package here
+    fspec = importlib.util.spec_from_file_location("ref_tests_fixtures", os.path.join(ref_shim.REFERENCE_ROOT, "tests", "fixtures.py"))
+    fixtures = importlib.util.module_from_spec(fspec)
+    fspec.loader.exec_module(fixtures)
+    saved_fixtures = sys.modules.get("tests.fixtures")
+    sys.modules["tests.fixtures"] = fixtures
+    try:
+        path = os.path.join(ref_shim.REFERENCE_ROOT, "tests", "units", "utilities", "test_dataframe_functions.py")
+        spec = importlib.util.spec_from_file_location("ref_test_dataframe_functions", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        names = ["test_with_wrong_input", "test_assert_single_row", "test_positive_rolling", "test_negative_rolling",
+                 "test_rolling_with_larger_shift", "test_stacked_rolling", "test_dict_rolling",
+                 "test_dict_rolling_maxshift_1", "test_order_rolling", "test_warning_on_non_uniform_time_steps"]
+        suite = unittest.TestSuite(mod.RollingTestCase(n) for n in names)
+        res = unittest.TextTestRunner(verbosity=0).run(suite)
+        assert res.testsRun == len(names) and res.wasSuccessful(), (res.failures, res.errors)
+    finally:
+        rdf.roll_time_series = original
+        if saved_fixtures is None:
+            sys.modules.pop("tests.fixtures", None)
+        else:
+            sys.modules["tests.fixtures"] = saved_fixtures

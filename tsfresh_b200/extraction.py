@@ -159,22 +159,51 @@ def _extract_rolled(rolled, default_fc_parameters, kind_to_fc_parameters, impute
     from . import dataframe_functions as _dff
     ctx = get_context(device)
     device_impute = impute_function is _dff.impute
-    blocks, columns = [], []
-    for kind in rolled.kinds:
+
+    def run(kind, values, begin, length, flags):
         fc = kind_to_fc_parameters[kind] if (kind_to_fc_parameters and kind in kind_to_fc_parameters) else default_fc_parameters
         plan = Plan(fc)
-        columns += [kind + "__" + s for s in plan.suffixes]
-        if plan.n_cols == 0 or len(rolled) == 0:
-            blocks.append(np.empty((len(rolled), plan.n_cols)))
-            continue
-        dp = _device_plan(ctx, plan)
+        names = [kind + "__" + s for s in plan.suffixes]
+        if plan.n_cols == 0 or len(begin) == 0:
+            return names, np.empty((len(begin), plan.n_cols))
+        return names, _device_plan(ctx, plan).extract_csr(values, begin, length, flags=flags)
+
+    if rolled.parts is None:                 # wide frame: every kind shares the windows
         flags = _lib.FLAG_IMPUTE if device_impute else 0          # columns are independent: per-kind impute is exact
-        blocks.append(dp.extract_csr(rolled.values[kind], rolled.begin, rolled.length, flags=flags))
-    data = blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1)
-    index = pd.Index(rolled.ids, tupleize_cols=False)
+        blocks, columns = [], []
+        for kind in rolled.kinds:
+            names, mat = run(kind, rolled.values[kind], rolled.begin, rolled.length, flags)
+            columns += names
+            blocks.append(mat)
+        data = blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1)
+        ids = rolled.ids
+        imputed = device_impute
+    else:                                    # kind column: every kind has its own windows; rows = union of the window ids
+        per = []
+        for kind, part in rolled.parts.items():
+            if len(part.values) != 1:
+                raise ValueError("Could not guess the value column! Please hand it to the function as an argument.")
+            names, mat = run(kind, next(iter(part.values.values())), part.begin, part.length, 0)
+            per.append((names, part.ids, mat))
+        ids = sorted(set().union(*[set(p[1]) for p in per]))
+        row = {w: r for r, w in enumerate(ids)}
+        columns = [n for p in per for n in p[0]]
+        data = np.full((len(ids), len(columns)), np.nan)
+        c0 = 0
+        for names, wids, mat in per:
+            data[[row[w] for w in wids], c0:c0 + len(names)] = mat
+            c0 += len(names)
+        imputed = False
+    index = pd.Index(ids, tupleize_cols=False)
     result = pd.DataFrame(data, index=index, columns=columns, copy=False)
-    if impute_function is not None and not device_impute:
-        impute_function(result)
+    if impute_function is not None and not imputed:
+        if device_impute:
+            if result.shape[0] and result.shape[1]:
+                m = np.ascontiguousarray(result.to_numpy(dtype=np.float64))
+                ctx.impute(m, _lib.IMPUTE_RANGE)
+                result = pd.DataFrame(m, index=result.index, columns=result.columns, copy=False)
+        else:
+            impute_function(result)
     return result
 
 

@@ -25,7 +25,10 @@ class RolledTimeSeries:
     """Windows of one frame: `values[kind]` float32 in (id, sort) order, `begin/length` per window, `ids` = list of
     `(original id, sort value of the row that names the window)` in the order the reference's result is sorted."""
 
-    def __init__(self, values, begin, length, ids, parent, id_row, sort_values, column_sort):
+    def __init__(self, values, begin, length, ids, parent, id_row, sort_values, column_sort, parts=None,
+                 column_kind=None):
+        self.parts = parts                # long format with a kind column: kind -> RolledTimeSeries of that kind's rows
+        self.column_kind = column_kind
         self.values = values              # dict kind -> float32 array
         self.begin = begin
         self.length = length
@@ -36,14 +39,23 @@ class RolledTimeSeries:
         self.column_sort = column_sort
 
     def __len__(self):
-        return len(self.begin)
+        return len(self.begin) if self.parts is None else sum(len(p) for p in self.parts.values())
 
     @property
     def kinds(self):
-        return list(self.values.keys())
+        return list(self.values.keys()) if self.parts is None else list(self.parts.keys())
 
     def to_frame(self):
         """The reference's rolled DataFrame (rows copied once per window): columns id, sort column, one per kind."""
+        if self.parts is not None:
+            frames = []
+            for kind, part in self.parts.items():
+                f = part.to_frame()
+                f[self.column_kind] = kind
+                frames.append(f)
+            out = pd.concat(frames, ignore_index=True)
+            # the reference concatenates its per-shift chunks and sorts by (id, sort) with a stable multi-key sort
+            return out.sort_values(by=["id", self.column_sort or "sort"], kind="stable").reset_index(drop=True)
         rows = np.concatenate([np.arange(b, b + n) for b, n in zip(self.begin, self.length)]) if len(self) else np.zeros(0, np.int64)
         out = {"id": np.repeat(np.arange(len(self)), self.length)}
         ids = np.empty(len(self), dtype=object)
@@ -78,10 +90,21 @@ def roll_time_series(df_or_dict, column_id, column_sort=None, column_kind=None, 
         raise ValueError("You have to set the column_id which contains the ids of the different time series")
     if column_id not in df:
         raise AttributeError("The given column for the id is not present in the data.")
-    if column_kind is not None:
-        raise NotImplementedError("roll_time_series views: pass one value column per kind (wide frame), not column_kind")
     if column_sort is not None and df[column_sort].isnull().any():
         raise ValueError("You have NaN values in your sort column.")
+    if column_kind is not None:
+        # long format with a kind column (:518-523): every (kind, id) group is rolled on its own, the shifts are
+        # anchored to the longest group of the whole frame
+        longest = int(df.groupby([column_kind, column_id]).size().max())
+        parts = {}
+        for kind, sub in df.groupby(column_kind, sort=True):
+            parts[str(kind)] = _roll_frame(sub.drop(columns=[column_kind]), column_id, column_sort, rolling_direction,
+                                           max_timeshift, min_timeshift, show_warnings, longest)
+        return RolledTimeSeries(None, None, None, None, None, None, None, column_sort, parts=parts, column_kind=column_kind)
+    return _roll_frame(df, column_id, column_sort, rolling_direction, max_timeshift, min_timeshift, show_warnings, None)
+
+
+def _roll_frame(df, column_id, column_sort, rolling_direction, max_timeshift, min_timeshift, show_warnings, longest):
 
     # series order: stable sort by (id, sort) -- skipped when the frame already is in that order
     ids_col = df[column_id].to_numpy()
@@ -105,9 +128,18 @@ def roll_time_series(df_or_dict, column_id, column_sort=None, column_kind=None, 
         d = np.diff(sort_col)[id_codes[1:] == id_codes[:-1]]
         if len(d) and d.min() != d.max():
             warnings.warn("Your time stamps are not uniformly sampled, which makes rolling nonsensical in some domains.")
-    longest = int(lens.max())
+    own_longest = int(lens.max())
+    longest = own_longest if longest is None else int(longest)
     mx = int(max_timeshift) if max_timeshift else longest                 # `max_timeshift or prediction_steps` (:552)
-    wb, wl, wp, we = _lib.roll_windows(begin, lens, int(rolling_direction), mx, int(min_timeshift))
+    if longest > own_longest:
+        # the shifts are anchored to the longest group of the WHOLE frame: a phantom series of that length (its
+        # windows are dropped again) makes tsfx_roll_windows use it
+        wb, wl, wp, we = _lib.roll_windows(np.append(begin, 0), np.append(lens, np.int32(longest)), int(rolling_direction),
+                                           mx, int(min_timeshift))
+        keep = wp < len(lens)
+        wb, wl, wp, we = wb[keep], wl[keep], wp[keep], we[keep]
+    else:
+        wb, wl, wp, we = _lib.roll_windows(begin, lens, int(rolling_direction), mx, int(min_timeshift))
 
     value_cols = [c for c in df.columns if c not in keys]
     values = {}
