@@ -187,3 +187,19 @@ def test_id_sharding_and_gather_world_size_2(n_rows):
         p.join(timeout=60)
     assert [r[3] for r in res] == [True, True]
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == n_rows      # contiguous, covering
+
+
+def test_impute_helpers_validate_before_touching_the_device():
+    """impute_dataframe_range raises the reference's ValueErrors (dataframe_functions.py:136-156) and the helpers
+    return empty frames untouched (:71-72, :93-94, :133-134) -- all before any device call."""
+    import pandas as pd
+    from tsfresh_b200 import impute, impute_dataframe_range, impute_dataframe_zero
+    df = pd.DataFrame({"a": [1.0, np.nan], "b": [np.inf, 2.0]})
+    good = {"a": 1.0, "b": 2.0}
+    with pytest.raises(ValueError, match="more or less keys"):
+        impute_dataframe_range(df, {"a": 1.0}, good, good)
+    with pytest.raises(ValueError, match="non finite values"):
+        impute_dataframe_range(df, good, {"a": np.nan, "b": 0.0}, good)
+    empty = pd.DataFrame(columns=["a", "b"], dtype=float)
+    assert impute(empty) is empty and impute_dataframe_zero(empty) is empty
+    assert impute_dataframe_range(empty, good, good, good) is empty
