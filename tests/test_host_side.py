@@ -189,6 +189,26 @@ def test_id_sharding_and_gather_world_size_2(n_rows):
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == n_rows      # contiguous, covering
 
 
+def test_window_sharding_keeps_parents_together():
+    """distributed.shard_windows: config-5 layout -- contiguous, complete, no parent split over two ranks."""
+    from tsfresh_b200 import distributed as D
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for n_par in (1, 2, 5, 40):
+            counts = rng.integers(0, 9, n_par)
+            parent = np.repeat(np.arange(n_par), counts)
+            spans = [D.shard_windows(parent, n_par, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == len(parent)
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            owners = {}
+            for r, (lo, hi) in enumerate(spans):
+                for p in set(parent[lo:hi].tolist()):
+                    assert owners.setdefault(p, r) == r
+    # the benchmark shape: 10 000 parents x 121 windows over 8 ranks -> 1250 parents each
+    parent = np.repeat(np.arange(10000), 121)
+    assert [D.shard_windows(parent, 10000, 8, r) for r in range(8)] == [(r * 151250, (r + 1) * 151250) for r in range(8)]
+
+
 def test_impute_helpers_validate_before_touching_the_device():
     """impute_dataframe_range raises the reference's ValueErrors (dataframe_functions.py:136-156) and the helpers
     return empty frames untouched (:71-72, :93-94, :133-134) -- all before any device call."""

@@ -55,3 +55,25 @@ def extract_dense_sharded(values, fc_parameters, device=None, group=None):
     dev = torch.device("cuda", ctx.device)
     full = gather_rows(torch.from_numpy(local).to(dev), n, group)
     return plan.suffixes, full
+
+
+def shard_windows(parent, n_parents, world, rank):
+    """Rolled windows (tsfresh_b200.rolling / tsfx_roll_windows) shard by PARENT series so that a window never
+    straddles ranks: contiguous parent ranges with as equal window counts as whole parents allow.
+    `parent[w]` is the (ascending) parent index of window w.  Returns (lo, hi): this rank owns windows [lo, hi)."""
+    import numpy as np
+    parent = np.asarray(parent)
+    n = len(parent)
+    if n == 0:
+        return 0, 0
+    # first window of every parent that has windows, and the ideal split points in window units
+    starts = np.flatnonzero(np.concatenate([[True], parent[1:] != parent[:-1]]))
+    cuts = [0]
+    for r in range(1, world):
+        target = (n * r) // world
+        k = int(np.searchsorted(starts, target, side="left"))     # next parent boundary at or after the target
+        cuts.append(int(starts[k]) if k < len(starts) else n)
+    cuts.append(n)
+    for r in range(1, len(cuts)):                                 # monotone (small inputs: several ranks may be empty)
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return cuts[rank], cuts[rank + 1]
