@@ -223,3 +223,40 @@ def test_impute_helpers_validate_before_touching_the_device():
     empty = pd.DataFrame(columns=["a", "b"], dtype=float)
     assert impute(empty) is empty and impute_dataframe_zero(empty) is empty
     assert impute_dataframe_range(empty, good, good, good) is empty
+
+
+def test_input_validation_matches_reference_wrong_input_cases():
+    """The pandas cases of the reference's DataAdapterTestCase.test_with_wrong_input
+    (tests/units/feature_extraction/test_data.py:459-548) against the adapters of tsfresh_b200.extract_features
+    (`_frames`, restating data.py:124-338): every malformed container raises ValueError before any device work."""
+    import pandas as pd
+    from tsfresh_b200.extraction import _frames
+
+    def to_tsdata(df, column_id, column_kind, column_value, column_sort):
+        return _frames(df, column_id, column_kind, column_value, column_sort)
+
+    bad = [
+        (pd.DataFrame([{"id": 0, "kind": "a", "value": 3, "sort": np.nan}]), "id", "kind", "value", "sort"),
+        (pd.DataFrame([{"id": 0, "kind": "a", "value": 3, "sort": 1}]), "strange_id", "kind", "value", "sort"),
+        (pd.DataFrame([{"id": 0, "kind": "a", "value": 3, "value_2": 1, "sort": 1}]), "strange_id", "kind", None, "sort"),
+        (pd.DataFrame([{"id": 0, "kind": "a", "value": 3, "sort": 1}]), "id", "strange_kind", "value", "sort"),
+        (pd.DataFrame([{"id": np.nan, "kind": "a", "value": 3, "sort": 1}]), "id", "kind", "value", "sort"),
+        (pd.DataFrame([{"id": 0, "kind": np.nan, "value": 3, "sort": 1}]), "id", "kind", "value", "sort"),
+        (pd.DataFrame([{"id": 2}, {"id": 1}]), None, "a", "b", None),
+        (pd.DataFrame([{"id": 2}, {"id": 1}]), None, "a", "b", "a"),
+        ({"a": pd.DataFrame([{"id": 2}, {"id": 1}]), "b": pd.DataFrame([{"id": 2}, {"id": 1}])}, None, "a", "b", None),
+        ({"a": pd.DataFrame([{"id": 2}, {"id": 1}]), "b": pd.DataFrame([{"id": 2}, {"id": 1}])}, "id", None, None, None),
+        ({"a": pd.DataFrame([{"id": 2, "value_a": 3}, {"id": 1, "value_a": 4}]), "b": pd.DataFrame([{"id": 2}, {"id": 1}])},
+         "id", None, None, None),
+        (pd.DataFrame([{"id": 0, "value": np.nan}]), "id", None, "value", None),
+        (pd.DataFrame([{"id": 0, "value": np.nan}]), None, None, "value", None),
+        (pd.DataFrame([{"id": 0, "a_": 3, "b": 5, "sort": 1}]), "id", None, None, "sort"),
+        (pd.DataFrame([{"id": 0, "a__c": 3, "b": 5, "sort": 1}]), "id", None, None, "sort"),
+        (pd.DataFrame([{"id": 0}]), "id", None, None, None),
+        (pd.DataFrame([{"id": 0, "sort": 0}]), "id", None, None, "sort"),
+        ([1, 2, 3], "a", "b", "c", "d"),
+    ]
+    for k, case in enumerate(bad):
+        with pytest.raises(ValueError):
+            to_tsdata(*case)
+            pytest.fail("case %d did not raise" % k)
