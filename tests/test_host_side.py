@@ -57,6 +57,26 @@ def test_plan_rejects_what_has_no_gpu_path():
     assert p.suffixes == ["ar_coefficient__coeff_1__k_3", "maximum"]
 
 
+def test_from_columns_round_trip():
+    """from_columns(column names) -> settings whose plan produces exactly those columns (settings.py:23-83; the
+    reference pins the same round trip in tests/units/feature_extraction/test_settings.py:100-117)."""
+    from tsfresh_b200 import ComprehensiveFCParameters, from_columns
+    suffixes = Plan(ComprehensiveFCParameters()).suffixes
+    k2 = from_columns(["value__" + s for s in suffixes] + ["b__maximum", "b__quantile__q_0.9", "junk"], columns_to_ignore=["junk"])
+    assert list(k2) == ["value", "b"] and k2["b"] == {"maximum": None, "quantile": [{"q": 0.9}]}
+    assert sorted(Plan(k2["value"]).suffixes) == sorted(suffixes)
+    sub = [s for s in suffixes if s.startswith(("fft_coefficient", "agg_linear_trend", "value_count", "mean"))]
+    assert sorted(Plan(from_columns(["x__" + s for s in sub])["x"]).suffixes) == sorted(sub)
+    cfg = from_columns(["x__value_count__value_nan", "x__range_count__max_inf__min_-inf"])["x"]
+    assert np.isnan(cfg["value_count"][0]["value"]) and cfg["range_count"] == [{"max": np.inf, "min": -np.inf}]
+    with pytest.raises(ValueError):
+        from_columns(["nounderscore"])
+    with pytest.raises(TypeError):
+        from_columns([3])
+    with pytest.raises(ValueError):
+        from_columns(["value__not_a_calculator"])
+
+
 def test_roll_windows_match_reference_roll_time_series():
     z = np.load(os.path.join(G, "roll.npz"))
     lens = z["lens"].astype(np.int32)

@@ -162,3 +162,25 @@ def test_reference_rolling_test_cases_pass_on_the_view_implementation():
             sys.modules.pop("tests.fixtures", None)
         else:
             sys.modules["tests.fixtures"] = saved_fixtures
+
+
+def test_from_columns_matches_reference():
+    """settings.from_columns (settings.py:23-83): same kind_to_fc_parameters and same errors as the reference."""
+    ref_shim.load()
+    from tsfresh.feature_extraction import settings as rs
+    from tsfresh_b200.settings import from_columns
+    cols = (["value__" + s for s in Plan(ComprehensiveFCParameters()).suffixes]
+            + ["other__maximum", "other__quantile__q_0.25", 'k__agg_linear_trend__attr_"slope"__chunk_len_5__f_agg_"max"',
+               "k__value_count__value_nan", "k__range_count__max_inf__min_-inf", "k__fft_coefficient__attr_\"abs\"__coeff_3"])
+    mine = from_columns(cols + ["skipme"], columns_to_ignore=["skipme"])
+    ref = rs.from_columns(cols + ["skipme"], columns_to_ignore=["skipme"])
+
+    def norm(d):
+        return {k: {f: (None if p is None else [tuple(sorted((a, repr(b)) for a, b in q.items())) for q in p])
+                    for f, p in v.items()} for k, v in d.items()}
+    assert norm(mine) == norm(ref) and list(mine) == list(ref)
+    for bad, err in ((["nounderscore"], ValueError), ([3], TypeError), (["value__not_a_calculator"], ValueError)):
+        with pytest.raises(err):
+            from_columns(bad)
+        with pytest.raises(err):
+            rs.from_columns(bad)

@@ -114,3 +114,58 @@ class EfficientFCParameters(ComprehensiveFCParameters):
         super().__init__()
         for k in [k for k in self.data if k in HIGH_COMP_COST]:
             del self.data[k]
+
+
+# ------------------------------------------------------------------ column names -> settings (settings.py:23-83)
+def get_config_from_string(parts):
+    """Inverse of the feature-name grammar (utilities/string_manipulation.py:10-44): `parts` is a column name split
+    on "__"; everything after <kind>, <calculator> is `<parameter name>_<python literal>`.  None without parameters."""
+    import ast
+
+    import numpy as np
+    if len(parts) <= 2:
+        return None
+    config = {}
+    for piece in parts[2:]:
+        key, value = piece.rsplit("_", 1)
+        low = value.lower()
+        if low == "nan":
+            config[key] = np.nan
+        elif low == "-inf":
+            config[key] = -np.inf
+        elif low == "inf":
+            config[key] = np.inf
+        else:
+            config[key] = ast.literal_eval(value)
+    return config
+
+
+def from_columns(columns, columns_to_ignore=None):
+    """`kind_to_fc_parameters` that extracts exactly the features named in `columns` (the reference's
+    tsfresh.feature_extraction.settings.from_columns, settings.py:23-83: typically the columns a feature selection
+    kept).  Same errors: TypeError for a non-string column, ValueError for a name without "__" or an unknown
+    calculator."""
+    from .plan import CALC
+    ignore = set(columns_to_ignore or [])
+    kind_to_fc_parameters = {}
+    for col in columns:
+        if col in ignore:
+            continue
+        if not isinstance(col, str):
+            raise TypeError("Column name {} should be a string or unicode".format(col))
+        parts = col.split("__")
+        if len(parts) == 1:
+            raise ValueError("Splitting of columnname {} resulted in only one part.".format(col))
+        kind, feature_name = parts[0], parts[1]
+        per_kind = kind_to_fc_parameters.setdefault(kind, {})
+        if "TSFX_" + feature_name.upper() not in CALC or feature_name == "const_nan":
+            raise ValueError("Unknown feature name {}".format(feature_name))
+        config = get_config_from_string(parts)
+        if config:
+            per_kind.setdefault(feature_name, [])
+            if per_kind[feature_name] is None:
+                per_kind[feature_name] = []
+            per_kind[feature_name].append(config)
+        else:
+            per_kind[feature_name] = None
+    return kind_to_fc_parameters
