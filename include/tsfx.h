@@ -27,13 +27,14 @@
 #ifndef TSFX_H_
 #define TSFX_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define TSFX_VERSION 1
+#define TSFX_VERSION 2
 
 /* error codes */
 #define TSFX_OK 0
@@ -47,7 +48,9 @@ extern "C" {
 /* flags */
 #define TSFX_FLAG_DEVICE_PTRS 1u /* values/begin/len/out are device pointers; async on ctx stream */
 #define TSFX_FLAG_TIMING 2u      /* record CUDA events around every kernel group (tsfx_get_timings) */
-#define TSFX_FLAG_NO_NAN_CHECK 4u
+#define TSFX_FLAG_NO_NAN_CHECK 4u /* host-pointer extract calls scan the values for NaN and return TSFX_E_NAN (the reference
+                                  * raises ValueError, data.py:148-167); this flag skips the scan.  Device-pointer calls
+                                  * (asynchronous) never scan. */
 #define TSFX_FLAG_IMPUTE 8u      /* extract calls: impute the feature matrix on the device before it is returned
                                   * (extract_features(impute_function=impute), extraction.py:179-181, 286-287) */
 #define TSFX_FLAG_ALL_MEDIANS 16u /* tsfx_impute: compute every column's median, not only those a NaN needs */
@@ -186,14 +189,50 @@ int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values
 
 /* Long frame (stage (a)): rows (ids[i], sort_keys[i], values[i]) in any order.  Groups rows by id,
  * orders each group by sort key (stable for equal keys; sort_keys may be NULL = keep row order), then
- * extracts.  Series come out in ascending id order: out_ids[s] and row s of out.  Host pointers only.
+ * extracts.  Series come out in ascending id order: out_ids[s] and row s of out.
  * sort_key_is_f64: 0 = int64 keys, 1 = float64 keys.  Returns the number of series in *n_series_out;
- * TSFX_E_INVALID if it exceeds out_capacity.  Two-step use: call tsfx_build_csr with all output
- * pointers NULL (it counts the series and keeps the CSR on the device), size `out`, then call
- * tsfx_extract_long with ids == values == NULL to extract from the held CSR without sorting again. */
+ * TSFX_E_INVALID if it exceeds out_capacity.
+ * Rows that already arrive ordered by (id, sort key) take the pipelined path: one pass over the id column, one host
+ * synchronisation for the sizes, then the sort-key / value columns are copied in row blocks while the kernels of the
+ * previous blocks run and their result rows travel back.  Any other order is sorted on the device first.
+ * Host pointers may be pageable (staged through pinned memory by worker threads) or page-locked.  With
+ * TSFX_FLAG_DEVICE_PTRS every pointer (ids, sort_keys, values, out_ids, out) is a device pointer; the call still
+ * synchronises once to learn the sizes.
+ * Two-step use: call tsfx_build_csr with all output pointers NULL (it counts the series and keeps the CSR on the
+ * device), size `out`, then call tsfx_extract_long with ids == values == NULL to extract from the held CSR. */
 int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
                       int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t* out_ids,
                       double* out, int64_t out_capacity, int64_t* n_series_out, uint32_t flags);
+
+/* Same, but the library sizes the result itself: *out ([n_series x n_cols] float64) and *out_ids come from the context's
+ * pinned host pool and must be handed back with tsfx_host_free (a numpy array can wrap them without a copy). */
+int tsfx_extract_long_alloc(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
+                            int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t** out_ids,
+                            double** out, int64_t* n_series_out, uint32_t flags);
+
+/* Page-locked host memory from the context's pool (freed blocks are cached: page-locking is slow). */
+void* tsfx_host_alloc(tsfx_ctx* ctx, size_t bytes);
+void tsfx_host_free(tsfx_ctx* ctx, void* p);
+
+/* Multi-GPU result placement -- replaces the single all-gather of the feature matrix (the
+ * reference's workers return their rows to the parent process, distribution.py:471-486).  peer_out[p] is rank p's copy
+ * of the full result matrix as mapped into THIS process (CUDA IPC / symmetric memory), peer_out[self_index] the local
+ * one.  Afterwards every device-pointer extract call whose `out` lies inside the local matrix also places its rows at
+ * the same offset of every peer's matrix:
+ *   TSFX_PEER_COPY       copy engines (cudaMemcpyAsync over NVLink on a side stream, no SM time), per row block
+ *   TSFX_PEER_STORE      the assemble kernel stores each finished row to every peer (P2P stores over NVLink)
+ *   TSFX_PEER_MULTICAST  the assemble kernel stores each row once through `multicast_out`, the multicast mapping of the
+ *                        matrix (NVSwitch replicates the store to all ranks, this one included)
+ *   TSFX_PEER_AUTO       MULTICAST when multicast_out != 0, else COPY
+ * tsfx_peer_flush makes the context's stream wait for the copies in flight; the caller then synchronises the ranks
+ * (barrier) before reading its matrix.  n_peers = 0 switches the placement off. */
+#define TSFX_PEER_AUTO 0
+#define TSFX_PEER_COPY 1
+#define TSFX_PEER_STORE 2
+#define TSFX_PEER_MULTICAST 3
+int tsfx_set_peer_outputs(tsfx_ctx* ctx, const uint64_t* peer_out, int32_t n_peers, int32_t self_index,
+                          uint64_t multicast_out, int32_t mode);
+int tsfx_peer_flush(tsfx_ctx* ctx);
 
 /* Stage (a) alone: builds the CSR on the device (it stays held by the context until the next stage-(a)
  * call) and copies back whichever outputs are non-NULL. */

@@ -3,6 +3,7 @@ cannot create a context on a CUDA device, every entry point raises."""
 import ctypes
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -13,8 +14,10 @@ LIB_PATH = os.path.join(HERE, "libtsfx.so")
 
 FLAG_DEVICE_PTRS = 1
 FLAG_TIMING = 2
+FLAG_NO_NAN_CHECK = 4
 FLAG_IMPUTE = 8
 FLAG_ALL_MEDIANS = 16
+PEER_AUTO, PEER_COPY, PEER_STORE, PEER_MULTICAST = 0, 1, 2, 3
 IMPUTE_RANGE, IMPUTE_ZERO, IMPUTE_GIVEN, IMPUTE_STATS = 0, 1, 2, 3
 
 _ERR = {-1: ValueError, -2: RuntimeError, -3: NotImplementedError, -4: ValueError, -5: MemoryError, -6: ValueError}
@@ -25,7 +28,8 @@ _lock = threading.Lock()
 EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync", "tsfx_version",
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
-           "tsfx_last_launch_count", "tsfx_impute"]
+           "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
+           "tsfx_set_peer_outputs", "tsfx_peer_flush"]
 
 
 def load():
@@ -34,9 +38,9 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        if not os.path.exists(LIB_PATH) or os.path.exists(_build.NVCC):
+            _build.build()               # no-op when the stamp matches the sources; a box without nvcc uses the shipped .so
         lib = ctypes.CDLL(LIB_PATH)
         vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
         lib.tsfx_ctx_create.argtypes = [ctypes.c_int, vp, ctypes.POINTER(vp)]
@@ -57,6 +61,14 @@ def load():
         lib.tsfx_get_timings.argtypes = [vp, vp, vp, i32]
         lib.tsfx_last_launch_count.argtypes = [vp]
         lib.tsfx_impute.argtypes = [vp, vp, i64, i32, i32, vp, u32]
+        lib.tsfx_extract_long_alloc.argtypes = [vp, vp, vp, vp, i32, vp, i64, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                ctypes.POINTER(i64), u32]
+        lib.tsfx_host_alloc.argtypes = [vp, ctypes.c_size_t]
+        lib.tsfx_host_alloc.restype = vp
+        lib.tsfx_host_free.argtypes = [vp, vp]
+        lib.tsfx_host_free.restype = None
+        lib.tsfx_set_peer_outputs.argtypes = [vp, vp, i32, i32, ctypes.c_uint64, i32]
+        lib.tsfx_peer_flush.argtypes = [vp]
         _lib = lib
         return lib
 
@@ -77,6 +89,9 @@ class Context:
         self.h = h
         self.device = int(device)
         self._plans = {}
+        # the context owns device scratch that every entry point reuses: calls on one context are serialised
+        # (include/tsfx.h "Threading"); ctypes releases the GIL, so the lock is needed for multi-threaded callers
+        self.lock = threading.RLock()
 
     def close(self):
         if getattr(self, "h", None):
@@ -122,14 +137,44 @@ class Context:
             stats = np.full((3, cols), np.nan) if col_stats is None else np.ascontiguousarray(col_stats, dtype=np.float64)
             if stats.shape != (3, cols):
                 raise ValueError("col_stats must have shape (3, n_cols)")
-        rc = self.lib.tsfx_impute(self.h, _ptr(matrix), rows, cols, mode, _ptr(stats),
-                                  FLAG_ALL_MEDIANS if all_medians else 0)
-        self.check(rc, "tsfx_impute")
+        with self.lock:
+            rc = self.lib.tsfx_impute(self.h, _ptr(matrix), rows, cols, mode, _ptr(stats),
+                                      FLAG_ALL_MEDIANS if all_medians else 0)
+            self.check(rc, "tsfx_impute")
         return stats
 
     def impute_device(self, matrix_ptr, rows, cols, mode=IMPUTE_RANGE):
         rc = self.lib.tsfx_impute(self.h, ctypes.c_void_p(matrix_ptr), rows, cols, mode, None, FLAG_DEVICE_PTRS)
         self.check(rc, "tsfx_impute")
+
+    # ---- pinned host memory (tsfx_host_alloc): numpy arrays the device can copy to / from at full PCIe speed
+    def pinned_array(self, shape, dtype):
+        """numpy array on page-locked memory from the context's pool; the block returns to the pool when the array
+        (and every view / DataFrame built on it) has been garbage collected."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = self.lib.tsfx_host_alloc(self.h, max(n, 1))
+        if not p:
+            raise MemoryError("tsfx_host_alloc(%d bytes) failed" % n)
+        return self._wrap_pinned(p, shape, dtype)
+
+    def _wrap_pinned(self, p, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        buf = (ctypes.c_char * max(n, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        lib, h = self.lib, self.h
+        weakref.finalize(buf, lambda lib=lib, h=h, p=p: lib.tsfx_host_free(h, ctypes.c_void_p(p)))
+        return arr
+
+    # ---- multi-GPU result placement (tsfx_set_peer_outputs)
+    def set_peer_outputs(self, peer_ptrs, self_index, multicast_ptr=0, mode=PEER_AUTO):
+        arr = (ctypes.c_uint64 * max(1, len(peer_ptrs)))(*[int(x) for x in peer_ptrs])
+        rc = self.lib.tsfx_set_peer_outputs(self.h, arr, len(peer_ptrs), int(self_index), int(multicast_ptr), int(mode))
+        self.check(rc, "tsfx_set_peer_outputs")
+
+    def peer_flush(self):
+        self.check(self.lib.tsfx_peer_flush(self.h), "tsfx_peer_flush")
 
 
 class DevicePlan:
@@ -158,9 +203,10 @@ class DevicePlan:
         begin = np.ascontiguousarray(begin, dtype=np.int64)
         length = np.ascontiguousarray(length, dtype=np.int32)
         out = np.empty((len(begin), self.n_cols), dtype=np.float64)
-        rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, _ptr(values), values.size, _ptr(begin), _ptr(length),
-                                           len(begin), _ptr(out), flags)
-        self.ctx.check(rc, "tsfx_extract_csr")
+        with self.ctx.lock:
+            rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, _ptr(values), values.size, _ptr(begin), _ptr(length),
+                                               len(begin), _ptr(out), flags)
+            self.ctx.check(rc, "tsfx_extract_csr")
         return out
 
     def extract_dense(self, values2d, flags=0, out=None):
@@ -168,11 +214,14 @@ class DevicePlan:
         n, L = values2d.shape
         if out is None:
             out = np.empty((n, self.n_cols), dtype=np.float64)
-        rc = self.ctx.lib.tsfx_extract_dense(self.ctx.h, self.h, _ptr(values2d), n, L, _ptr(out), flags)
-        self.ctx.check(rc, "tsfx_extract_dense")
+        with self.ctx.lock:
+            rc = self.ctx.lib.tsfx_extract_dense(self.ctx.h, self.h, _ptr(values2d), n, L, _ptr(out), flags)
+            self.ctx.check(rc, "tsfx_extract_dense")
         return out
 
     def extract_long(self, ids, sort_keys, values, flags=0):
+        """(id, sort key, value) rows in any order -> (unique ids ascending, [n_ids x n_cols] matrix).  One C call
+        (tsfx_extract_long_alloc): the library sizes the result and returns it on pinned host memory."""
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         values = np.ascontiguousarray(values, dtype=np.float32)
         is_f64 = 0
@@ -184,19 +233,16 @@ class DevicePlan:
             else:
                 sort_keys = np.ascontiguousarray(sort_keys, dtype=np.int64)
         n_series = ctypes.c_int64(0)
-        lib, h = self.ctx.lib, self.ctx.h
-        # step 1: stage (a) on the device, count the series; step 2: size the result, extract from the held CSR
-        rc = lib.tsfx_build_csr(h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids), None, None, None, None,
-                                0, ctypes.byref(n_series))
-        self.ctx.check(rc, "tsfx_build_csr")
+        p_ids, p_out = ctypes.c_void_p(), ctypes.c_void_p()
+        ctx = self.ctx
+        with ctx.lock:
+            rc = ctx.lib.tsfx_extract_long_alloc(ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids),
+                                                 ctypes.byref(p_ids), ctypes.byref(p_out), ctypes.byref(n_series), flags)
+            ctx.check(rc, "tsfx_extract_long")
         k = n_series.value
-        out_ids = np.empty(k, dtype=np.int64)
-        out = np.empty((k, self.n_cols), dtype=np.float64)
-        if k:
-            rc = lib.tsfx_extract_long(h, self.h, None, None, 0, None, len(ids), _ptr(out_ids), _ptr(out), k,
-                                       ctypes.byref(n_series), flags)
-            self.ctx.check(rc, "tsfx_extract_long")
-        return out_ids, out
+        if k == 0 or not p_out.value:
+            return np.empty(0, dtype=np.int64), np.empty((0, self.n_cols), dtype=np.float64)
+        return ctx._wrap_pinned(p_ids.value, (k,), np.int64), ctx._wrap_pinned(p_out.value, (k, self.n_cols), np.float64)
 
     # ---- device-pointer entry points (torch tensors own the memory) ----------------------------
     def extract_dense_device(self, values_ptr, n_series, length, out_ptr, timing=False):
@@ -231,9 +277,10 @@ def build_csr(ctx, ids, sort_keys, values):
     length = np.empty(n, dtype=np.int32)
     sv = np.empty(n, dtype=np.float32)
     k = ctypes.c_int64(0)
-    rc = ctx.lib.tsfx_build_csr(ctx.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), n, _ptr(uid), _ptr(begin),
-                                _ptr(length), _ptr(sv), n, ctypes.byref(k))
-    ctx.check(rc, "tsfx_build_csr")
+    with ctx.lock:
+        rc = ctx.lib.tsfx_build_csr(ctx.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), n, _ptr(uid), _ptr(begin),
+                                    _ptr(length), _ptr(sv), n, ctypes.byref(k))
+        ctx.check(rc, "tsfx_build_csr")
     k = k.value
     return uid[:k].copy(), begin[:k].copy(), length[:k].copy(), sv
 

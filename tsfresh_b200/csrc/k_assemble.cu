@@ -2,6 +2,8 @@
 // (the dense float64 result PartitionedTsData.pivot would build, tsfresh/feature_extraction/data.py:86-121).
 // One warp per row: coalesced reads of the staging rows into shared memory at their final column,
 // then one coalesced write of the whole row.  Pure HBM traffic: 16 bytes per feature value.
+// Multi-GPU: the same row is also stored into the peers' result matrices (NVLink P2P stores or one multicast store),
+// which replaces the all-gather of SURVEY.md section 8e -- no collective kernel, no extra pass over the matrix.
 #include <algorithm>
 
 #include "tsfx_common.cuh"
@@ -25,8 +27,19 @@ __global__ void __launch_bounds__(WPC * 32) k_assemble(AssembleArgs A, int row_p
             for (int j = lane; j < w; j += 32) row[__ldg(A.final_col + c0 + j)] = __ldcs(src + j);
         }
         __syncwarp();
-        double* dst = A.out + (size_t)s * A.ncols;
-        for (int j = lane; j < A.ncols; j += 32) __stcs(dst + j, row[j]);
+        const size_t roff = (size_t)s * A.ncols;
+        if (A.out_mc) {
+            double* dst = A.out_mc + roff;
+            for (int j = lane; j < A.ncols; j += 32)
+                asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst + j), "d"(row[j]) : "memory");
+        } else {
+            double* dst = A.out + roff;
+            for (int j = lane; j < A.ncols; j += 32) __stcs(dst + j, row[j]);
+        }
+        for (int p = 0; p < A.n_extra; ++p) {
+            double* dst = A.extra[p] + roff;
+            for (int j = lane; j < A.ncols; j += 32) __stcs(dst + j, row[j]);
+        }
         __syncwarp();
     }
 }

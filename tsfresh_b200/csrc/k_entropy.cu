@@ -203,14 +203,269 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 3 : 1)) k_entropy(Entrop
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Rank-space formulation (default for series whose prefix table fits in shared memory).
+// Sort the series once (rank a <-> time index pi(a)).  For a tolerance tau the set { j : |x_i - x_j| <= tau } is a
+// CONTIGUOUS rank interval [lo, hi] around rank(i) (float64 subtraction of float32-origin values is monotone), so
+// the bit row of the bit-tile formulation needs no pair tests at all:
+//     R_i = T[hi + 1] & ~T[lo],      T[k] = { j : rank(j) < k }   (prefix bit vectors in TIME order, built once)
+// and the template counts stay popc(R_i & R_{i+1} >> 1 [& R_{i+2} >> 2]).  The interval ends come from two binary
+// searches per (row, tolerance) with exactly the predicate numpy evaluates ( fl64(x_a - x_b) <= tau ), so the counts
+// are bit-identical to the pair-test formulations above.  O(n^2 / 32) word operations + O(n log n) searches per
+// tolerance instead of O(n^2) float64 compares.
+// G warps work on one series (G = 1: warp per series; G > 1: the CTA is one series and shares the table).
+template <int G>
+__device__ __forceinline__ void gsync() { if (G == 1) __syncwarp(); else __syncthreads(); }
+
+__device__ __forceinline__ unsigned f32_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct RankLayout {            // byte offsets inside one series' working region
+    int t_off, s_off, pi_off, rk_off, lh_off, red_off, bytes;
+    int rs;                    // row stride of T in 32-bit words (multiple of 4, odd multiple of 16 bytes)
+};
+__host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
+    RankLayout L;
+    int n2 = 32;
+    while (n2 < nmax) n2 <<= 1;
+    const int W = (nmax + 31) >> 5;
+    int rs4 = (W + 3) >> 2;
+    if ((rs4 & 1) == 0) rs4 += 1;
+    L.rs = rs4 * 4;
+    int tb = (nmax + 1) * L.rs * 4;
+    if (tb < n2 * 8) tb = n2 * 8;                  // the sort keys alias the table
+    int o = 0;
+    L.t_off = o; o += (tb + 15) & ~15;
+    L.s_off = o; o += ((nmax + 1) * 8 + 15) & ~15;
+    L.pi_off = o; o += (n2 * 2 + 15) & ~15;
+    L.rk_off = o; o += ((nmax + 2) * 2 + 15) & ~15;
+    L.lh_off = o; o += (((nmax + 3) & ~3) * 4 + 15) & ~15;   // lo | (hi+1) << 16 per rank; aliases the float32 staging copy
+    L.red_off = o; o += (G > 1) ? G * 4 * 8 : 0;
+    L.bytes = (o + 15) & ~15;
+    return L;
+}
+
+template <int G, int SPC>
+__global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1))) k_entropy_rank(EntropyArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NTHR = G * 32;
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x / NTHR;                 // series slot inside the CTA
+    const int tid = threadIdx.x - grp * NTHR;           // thread inside the series group
+    const int gw = tid >> 5;                            // warp inside the series group
+    const RankLayout L = rank_layout(A.npad, G);
+    double* lnk = reinterpret_cast<double*>(smem_raw);                              // log(k), k = 0..npad (CTA-wide)
+    unsigned char* base = smem_raw + (((A.npad + 1) * 8 + 15) & ~15) + (size_t)grp * L.bytes;
+    unsigned* T = reinterpret_cast<unsigned*>(base + L.t_off);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + L.t_off);
+    double* s64 = reinterpret_cast<double*>(base + L.s_off);
+    unsigned short* pi = reinterpret_cast<unsigned short*>(base + L.pi_off);
+    unsigned short* rk = reinterpret_cast<unsigned short*>(base + L.rk_off);
+    unsigned* lohi = reinterpret_cast<unsigned*>(base + L.lh_off);
+    float* xs = reinterpret_cast<float*>(base + L.lh_off);
+    double* red = reinterpret_cast<double*>(base + L.red_off);
+    const int RS = L.rs;
+
+    for (int k = threadIdx.x; k <= A.npad; k += blockDim.x) lnk[k] = log((double)k);
+    __syncthreads();
+
+    const int64_t groups_total = (int64_t)gridDim.x * SPC;
+    int64_t s0 = (int64_t)blockIdx.x * SPC + grp;
+    // every group of a CTA runs the same number of trips when G > 1 (SPC == 1 there), so __syncthreads is safe
+    for (int64_t s = s0; s < A.R.n_series; s += groups_total) {
+        // ---- stage the series (every warp of the group keeps its own registers; xs is written once)
+        int64_t b; int n;
+        if (A.R.begin) { b = A.R.begin[s]; n = A.R.len[s]; } else { b = s * (int64_t)A.R.dense_len; n = A.R.dense_len; }
+        const float* src = A.R.values + b;
+        for (int i = tid; i < n; i += NTHR) xs[i] = __ldg(src + i);
+        gsync<G>();
+        const Moments M = moments(xs, n, nullptr, lane);          // identical in every warp of the group
+        int N2 = 32;
+        while (N2 < n) N2 <<= 1;
+        for (int i = tid; i < N2; i += NTHR)
+            keys[i] = i < n ? (((unsigned long long)f32_key(xs[i]) << 32) | (unsigned)i) : ~0ull;
+        gsync<G>();
+        // ---- bitonic sort by value (payload: time index)
+        for (int k = 2; k <= N2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (N2 >> 1); t += NTHR) {
+                    const int i = 2 * t - (t & (j - 1));
+                    const int l = i + j;
+                    const unsigned long long a = keys[i], c = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+                }
+                gsync<G>();
+            }
+        }
+        // sorted values (float64 for the searches), rank <-> time maps.  keys alias T: read everything before T is built
+        const int per = (n + NTHR - 1) / NTHR;
+        for (int q = 0; q < per; ++q) {
+            const int a = tid + q * NTHR;
+            unsigned long long kv = a < n ? keys[a] : 0ull;
+            if (a < n) {
+                const unsigned idx = (unsigned)kv;
+                s64[a] = (double)key_f32((unsigned)(kv >> 32));
+                pi[a] = (unsigned short)idx;
+                rk[idx] = (unsigned short)a;
+            }
+        }
+        gsync<G>();
+        // ---- prefix table T[k][w], k = 0..n: bit j of T[k] = [rank(j) < k]
+        const int W = (n + 31) >> 5;
+        const int Wr = ((W + 3) >> 2) << 2;                 // the main loop reads whole 16-byte chunks
+        {
+            int NC = NTHR / Wr;                              // k-chunks per word column
+            if (NC < 1) NC = 1;
+            const int CH = (n + NC - 1) / NC;                // rows per chunk (the last chunk also writes row n)
+            const int items = NC * Wr;
+            for (int it0 = (tid & ~31); it0 < items; it0 += NTHR) {      // warp-uniform trip count
+                unsigned init = 0u;
+                for (int u = 0; u < 32; ++u) {               // starting words by ballot: 32 items per warp pass
+                    const int item = it0 + u;
+                    if (item >= items) break;
+                    const int w = item % Wr, c = item / Wr;
+                    const int j = 32 * w + lane;
+                    const bool below = j < n && (int)rk[j] < c * CH;
+                    const unsigned v = __ballot_sync(FULL, below);
+                    if (lane == u) init = v;
+                }
+                const int item = it0 + lane;
+                if (item < items) {
+                    const int w = item % Wr, c = item / Wr;
+                    const int k0 = c * CH;
+                    int k1 = k0 + CH;
+                    if (k1 > n) k1 = n;
+                    unsigned cur = init;
+                    unsigned* col = T + w;
+                    for (int k = k0; k < k1; ++k) {
+                        col[(size_t)k * RS] = cur;
+                        const unsigned p = pi[k];
+                        if ((int)(p >> 5) == w) cur |= 1u << (p & 31);
+                    }
+                    if (k1 == n) col[(size_t)n * RS] = cur;      // row n (every rank below n): written by the chunk(s) ending there
+                }
+            }
+        }
+        gsync<G>();
+        double* orow = A.out + (size_t)s * A.ncols;
+        const int n2 = n - 1, n3 = n - 2;
+        int steps = 0;
+        while ((1 << steps) < n) ++steps;                    // search steps: 2^steps >= n
+        for (int dj = 0; dj < A.nd; ++dj) {
+            const Desc d = A.descs[dj];
+            const double tau = (d.calc == TSFX_SAMPLE_ENTROPY) ? 0.2 * M.sd : d.p0 * M.sd;
+            const bool sane = tau >= 0.0;                    // NaN / negative tolerance: every comparison is false
+            // ---- phase A: rank interval of every rank (two branch-free binary searches with numpy's predicate)
+            for (int r = tid; r < n; r += NTHR) {
+                unsigned v = 0x00010001u;                    // empty: T[1] & ~T[1]
+                if (sane) {
+                    const double sr = s64[r];
+                    int hi = r, lo = r;
+                    for (int st = steps - 1; st >= 0; --st) {
+                        const int c = hi + (1 << st);
+                        if (c < n && (s64[c] - sr) <= tau) hi = c;
+                        const int e = lo - (1 << st);
+                        if (e >= 0 && (sr - s64[e]) <= tau) lo = e;
+                    }
+                    v = (unsigned)lo | ((unsigned)(hi + 1) << 16);
+                }
+                lohi[r] = v;
+            }
+            gsync<G>();
+            // ---- phase B: template counts, lane = row (30 rows per block: rows i+1, i+2 come from the next lanes)
+            double l2 = 0.0, l3 = 0.0;
+            int iB = 0, iA = 0;
+            for (int r0 = gw * 30; r0 < n2; r0 += G * 30) {
+                const int i = r0 + lane;
+                const unsigned lh = i < n ? lohi[rk[i]] : 0x00010001u;
+                const uint4* Thi = reinterpret_cast<const uint4*>(T + (size_t)(lh >> 16) * RS);
+                const uint4* Tlo = reinterpret_cast<const uint4*>(T + (size_t)(lh & 0xffffu) * RS);
+                unsigned wp = 0u, s1p = 0u, s2p = 0u;
+                int c2 = 0, c3 = 0;
+#define TSFX_RANK_STEP(WN)                                                                     \
+                {                                                                              \
+                    const unsigned wn_ = (WN);                                                 \
+                    const unsigned s1n = __shfl_down_sync(FULL, wn_, 1), s2n = __shfl_down_sync(FULL, wn_, 2); \
+                    const unsigned m2 = wp & __funnelshift_r(s1p, s1n, 1);                     \
+                    const unsigned m3 = m2 & __funnelshift_r(s2p, s2n, 2);                     \
+                    c2 += __popc(m2);                                                          \
+                    c3 += __popc(m3);                                                          \
+                    wp = wn_; s1p = s1n; s2p = s2n;                                            \
+                }
+                for (int c = 0; c < (Wr >> 2); ++c) {
+                    const uint4 h = Thi[c], l = Tlo[c];
+                    TSFX_RANK_STEP(h.x & ~l.x)
+                    TSFX_RANK_STEP(h.y & ~l.y)
+                    TSFX_RANK_STEP(h.z & ~l.z)
+                    TSFX_RANK_STEP(h.w & ~l.w)
+                }
+                TSFX_RANK_STEP(0u)
+#undef TSFX_RANK_STEP
+                if (lane < 30 && i < n2) { l2 += lnk[c2]; iB += c2 - 1; }
+                if (lane < 30 && i < n3) { l3 += lnk[c3]; iA += c3 - 1; }
+            }
+            l2 = wsum(l2); l3 = wsum(l3);
+            double sB = (double)wsumi(iB), sA = (double)wsumi(iA);
+            if (G > 1) {
+                if (lane == 0) { red[gw * 4 + 0] = l2; red[gw * 4 + 1] = l3; red[gw * 4 + 2] = sB; red[gw * 4 + 3] = sA; }
+                __syncthreads();
+                l2 = 0.0; l3 = 0.0; sB = 0.0; sA = 0.0;
+                for (int w = 0; w < G; ++w) { l2 += red[w * 4 + 0]; l3 += red[w * 4 + 1]; sB += red[w * 4 + 2]; sA += red[w * 4 + 3]; }
+            }
+            l2 -= (double)n2 * log((double)n2);               // sum_i log(c_i / N) = sum_i log(c_i) - N log(N)
+            l3 -= n3 > 0 ? (double)n3 * log((double)n3) : 0.0;
+            double r;
+            if (d.calc == TSFX_SAMPLE_ENTROPY) r = -log(sA / sB);
+            else if (n <= 3) r = 0.0;                          // N <= m + 1
+            else r = fabs(l2 / (double)(n - 1) - l3 / (double)(n - 2));
+            if (tid == 0) orow[d.col] = r;
+            gsync<G>();                                        // lohi / red are rewritten by the next tolerance
+        }
+    }
+}
+
+// TSFX_ENTROPY = pairs | tiles | rank (default): which formulation counts the template matches
+static int entropy_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("TSFX_ENTROPY"); mode = !e ? 2 : (e[0] == 'p' ? 0 : (e[0] == 't' ? 1 : 2)); }
+    return mode;
+}
+
+template <int G, int SPC>
+static cudaError_t launch_rank(const EntropyArgs& A, size_t smem, int ctas_per_sm, cudaStream_t st, int sm_count) {
+    cudaError_t e = cudaFuncSetAttribute(k_entropy_rank<G, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (A.R.n_series + SPC - 1) / SPC;
+    const int64_t cap = (int64_t)sm_count * ctas_per_sm * grid_waves(16);
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    k_entropy_rank<G, SPC><<<(int)ctas, G * SPC * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, int sm_count) {
     EntropyArgs A = A0;
     A.npad = (max_len + 3) & ~3;
     A.xpad = ((A.npad + 2 + 31) / 32) * 32 + 32;          // NaN padding up to a whole 32-sample tile / 32-row block
-    {
-        static int mode = -1;
-        if (mode < 0) { const char* e = getenv("TSFX_ENTROPY"); mode = (e && e[0] == 'p') ? 0 : 1; }   // "pairs" = pair sweep
-        A.bittile = mode;
+    const int mode = entropy_mode();
+    A.bittile = mode != 0;
+    if (mode == 2 && max_len < 65000) {
+        // rank-space kernel: warp per series while four working regions fit three CTAs per SM, then 4 / 16 warps per
+        // series with the CTA sharing one prefix table; beyond that (n > ~1100) the pair-test tiles below take over
+        const size_t lnk = (((size_t)A.npad + 1) * 8 + 15) & ~(size_t)15;
+        const size_t s1 = lnk + 4 * (size_t)rank_layout(A.npad, 1).bytes;
+        const size_t s4 = lnk + (size_t)rank_layout(A.npad, 4).bytes;
+        const size_t s16 = lnk + (size_t)rank_layout(A.npad, 16).bytes;
+        if (s1 <= 75 * 1024) return launch_rank<1, 4>(A, s1, 3, st, sm_count);
+        if (s4 <= 55 * 1024) return launch_rank<4, 1>(A, s4, 4, st, sm_count);
+        if (s16 <= 226 * 1024) return launch_rank<16, 1>(A, s16, 1, st, sm_count);
     }
     size_t per = (size_t)A.xpad * 8 + (size_t)(A.npad + 4) * 8 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;

@@ -4,8 +4,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "tsfx_common.cuh"
@@ -56,6 +62,161 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// ---------------------------------------------------------------------------------- pinned host memory pool
+// Page-locking is slow (a few GB/s), so blocks handed back with tsfx_host_free are cached and reused.
+struct HostPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> idle;
+    std::unordered_map<void*, size_t> live;
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 1;
+        const size_t want = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = idle.lower_bound(want);
+            if (it != idle.end() && it->first <= want + want / 2 + ((size_t)64 << 20)) {
+                void* p = it->second;
+                live[p] = it->first;
+                idle.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            trim();                                  // give cached blocks back and retry once
+            if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        std::lock_guard<std::mutex> g(mu);
+        live[p] = want;
+        return p;
+    }
+    bool free(void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return false;
+        idle.emplace(it->second, p);
+        live.erase(it);
+        return true;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : idle) cudaFreeHost(kv.second);
+        idle.clear();
+    }
+    void release_all() {
+        trim();
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : live) cudaFreeHost(kv.first);
+        live.clear();
+    }
+};
+
+// ---------------------------------------------------------------------------------- pageable -> device staging
+// Host buffers that are not page-locked (numpy / pandas columns) are copied chunk by chunk into a ring of pinned
+// slots by a few worker threads (one memcpy thread cannot feed PCIe gen5) and sent with cudaMemcpyAsync, so the
+// transfer overlaps both the next chunk's memcpy and the kernels already queued.
+struct Stager {
+    static const int SLOTS = 3;
+    size_t slot_bytes = (size_t)32 << 20;
+    void* slot[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
+    bool busy[SLOTS] = {false, false, false};
+    int next = 0;
+    // worker pool
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    const char* src = nullptr;
+    char* dst = nullptr;
+    size_t total = 0, piece = 0;
+    int next_piece = 0, n_pieces = 0, pending = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || (generation != seen && next_piece < n_pieces); });
+            if (stop) return;
+            while (next_piece < n_pieces) {
+                const int k = next_piece++;
+                lk.unlock();
+                const size_t off = (size_t)k * piece;
+                memcpy(dst + off, src + off, std::min(piece, total - off));
+                lk.lock();
+                if (--pending == 0) cv_done.notify_all();
+            }
+            seen = generation;
+        }
+    }
+    void start(int n) {
+        if (!workers.empty()) return;
+        for (int i = 0; i < n; ++i) workers.emplace_back([this] { worker(); });
+    }
+    void parallel_copy(void* d, const void* s_, size_t bytes) {
+        if (workers.empty() || bytes < ((size_t)1 << 20)) { memcpy(d, s_, bytes); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        src = (const char*)s_; dst = (char*)d; total = bytes;
+        n_pieces = (int)std::min<size_t>(workers.size() * 2, (bytes + ((size_t)1 << 20) - 1) >> 20);
+        piece = ((bytes + n_pieces - 1) / n_pieces + 63) & ~(size_t)63;
+        n_pieces = (int)((bytes + piece - 1) / piece);
+        next_piece = 0; pending = n_pieces; ++generation;
+        cv.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    cudaError_t init() {
+        if (slot[0]) return cudaSuccess;
+        for (int i = 0; i < SLOTS; ++i) {
+            cudaError_t e = cudaHostAlloc(&slot[i], slot_bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        int n = (int)std::thread::hardware_concurrency();
+        const char* env = getenv("TSFX_COPY_THREADS");
+        n = env ? atoi(env) : std::min(8, std::max(1, n / 2));
+        if (n > 1) start(n);
+        return cudaSuccess;
+    }
+    void release() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : workers) t.join();
+        workers.clear();
+        for (int i = 0; i < SLOTS; ++i) { if (slot[i]) cudaFreeHost(slot[i]); if (ev[i]) cudaEventDestroy(ev[i]); slot[i] = nullptr; ev[i] = nullptr; }
+    }
+    // host (pageable or pinned) -> device, asynchronous with respect to the device; returns when the LAST chunk's
+    // cudaMemcpyAsync has been issued (pageable source: the source buffer is no longer needed by then)
+    cudaError_t h2d(void* d, const void* h, size_t bytes, cudaStream_t st) {
+        if (bytes == 0) return cudaSuccess;
+        cudaPointerAttributes at;
+        bool pinned = false;
+        if (cudaPointerGetAttributes(&at, h) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+        else cudaGetLastError();
+        if (pinned) return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+        cudaError_t e = init();
+        if (e != cudaSuccess) return e;
+        for (size_t off = 0; off < bytes; off += slot_bytes) {
+            const size_t cnt = std::min(slot_bytes, bytes - off);
+            const int k = next;
+            next = (next + 1) % SLOTS;
+            if (busy[k]) { e = cudaEventSynchronize(ev[k]); if (e != cudaSuccess) return e; }
+            parallel_copy(slot[k], (const char*)h + off, cnt);
+            e = cudaMemcpyAsync((char*)d + off, slot[k], cnt, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(ev[k], st);
+            if (e != cudaSuccess) return e;
+            busy[k] = true;
+        }
+        return cudaSuccess;
+    }
+};
+
 static const char* kGroupNames[G_EVENTS] = {"basic", "sorted", "spectral", "la", "entropy", "seq", "peaks", "assemble"};
 
 struct tsfx_ctx {
@@ -75,6 +236,15 @@ struct tsfx_ctx {
     CsrWorkspace csr;
     ImputeWorkspace imp;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
+    int held_max_len = 0;
+    HostPool pool;
+    Stager stager;
+    // multi-GPU result placement (tsfx_set_peer_outputs): peers' mapped result matrices
+    std::vector<uint64_t> peer_out;
+    int peer_self = -1, peer_mode = 0;
+    uint64_t peer_mc = 0;
+    cudaStream_t s_peer = nullptr;
+    cudaEvent_t ev_peer = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host path
     cudaStream_t s_side[3] = {nullptr, nullptr, nullptr};   // optional side streams so kernel groups can overlap
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -178,6 +348,8 @@ extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&ctx->s_peer, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_peer, cudaEventDisableTiming));
     for (int i = 0; i < 3; ++i) { CKC(cudaStreamCreateWithFlags(&ctx->s_side[i], cudaStreamNonBlocking)); CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     for (int i = 0; i < 2; ++i) { CKC(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
     // decimal threshold table d * 10^k (correctly rounded literals via strtod)
@@ -204,6 +376,10 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release(); ctx->stage.release();
     ctx->csr.release();
     ctx->imp.release();
+    ctx->stager.release();
+    ctx->pool.release_all();
+    if (ctx->s_peer) cudaStreamDestroy(ctx->s_peer);
+    if (ctx->ev_peer) cudaEventDestroy(ctx->ev_peer);
     if (ctx->d_dec) cudaFree(ctx->d_dec);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     for (int g = 0; g < G_EVENTS; ++g) { if (ctx->ev[g][0]) cudaEventDestroy(ctx->ev[g][0]); if (ctx->ev[g][1]) cudaEventDestroy(ctx->ev[g][1]); }
@@ -409,10 +585,14 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         const int sidx = launched++ % nstreams;
         cudaStream_t gs = (sidx == 0) ? ctx->stream : ctx->s_side[sidx - 1];
         const int g_ncols = (int)P->host[g].size();
+        // global working region: the whole buffer when the groups run back to back, a private slice per group when
+        // they overlap on side streams (concurrent groups must not share working sets)
+        const size_t slice = (nstreams > 1) ? (ctx->misc.cap / G_COUNT) & ~(size_t)255 : ctx->misc.cap;
+        unsigned char* const gs_base = (unsigned char*)ctx->misc.p + (nstreams > 1 ? (size_t)g * slice : 0);
         switch (g) {
             case G_BASIC: {
                 BasicArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.lag_needed = P->lag_needed;
                 A.nfin = P->basic_nfin;
                 int pac = P->pacf_want >= 0 ? 4 * (P->pacf_want + 1) : 0;
@@ -434,7 +614,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_SORTED: {
                 SortedArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = even(4 * (P->friedrich_r + 2) + 16);
                 A.nfin = P->sorted_nfin;
                 A.ncq = 0;
@@ -448,7 +628,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_SPECTRAL: {
                 SpectralArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.twiddle = ctx->d_tw; A.tw_n = ctx->tw_n;
                 A.tables = P->d_tables; A.table_off = P->d_toff; A.table_half = P->d_thalf;
                 A.need_fft = P->need_fft; A.need_welch = P->need_welch;
@@ -459,20 +639,20 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_LA: {
                 LaArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = P->max_ar_k;
                 e = launch_la(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_ENTROPY: {
                 EntropyArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 e = launch_entropy(A, max_len, gs, ctx->sm_count);
                 break;
             }
             case G_SEQ: {
                 SeqArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
                          (std::min(P->n_lz, 255) << 16);
                 e = launch_seq(A, max_len, gs, ctx->sm_count);
@@ -480,7 +660,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             }
             case G_PEAKS: {
                 SeqArgs A;
-                A.R = R; A.gscratch = (unsigned char*)ctx->misc.p; A.gscratch_bytes = ctx->misc.cap; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
+                A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_cwt_peaks_n << 8);
                 e = launch_peaks(A, max_len, gs, ctx->sm_count);
                 break;
@@ -503,15 +683,40 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         A.n_groups = G_COUNT;
         for (int g = 0; g <= G_COUNT; ++g) A.cum[g] = P->cum[g];
         A.final_col = P->d_final_col;
+        A.n_extra = 0;
+        A.out_mc = nullptr;
+        // multi-GPU placement: where does this row block live inside the peers' copies of the result matrix?
+        int64_t peer_off = -1;                 // byte offset of d_final inside this rank's mapped matrix
+        if (!ctx->peer_out.empty()) {
+            const uint64_t self = ctx->peer_out[ctx->peer_self];
+            if ((uint64_t)d_final < self) return fail(ctx, TSFX_E_INVALID, "out is not inside the matrix registered with tsfx_set_peer_outputs");
+            peer_off = (int64_t)((uint64_t)d_final - self);
+            if (ctx->peer_mode == TSFX_PEER_MULTICAST) A.out_mc = (double*)(ctx->peer_mc + (uint64_t)peer_off);
+            else if (ctx->peer_mode == TSFX_PEER_STORE)
+                for (size_t p = 0; p < ctx->peer_out.size(); ++p)
+                    if ((int)p != ctx->peer_self) A.extra[A.n_extra++] = (double*)(ctx->peer_out[p] + (uint64_t)peer_off);
+        }
         cudaError_t e = launch_assemble(A, ctx->stream, ctx->sm_count);
         if (e != cudaSuccess) return fail(ctx, TSFX_E_CUDA, std::string("launch assemble: ") + cudaGetErrorString(e));
         ctx->launches += 1;
         if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][1], ctx->stream)); ctx->ev_used[G_COUNT] = true; }
+        if (peer_off >= 0 && ctx->peer_mode == TSFX_PEER_COPY) {
+            // copy engines push the finished row block to every peer while the next block's kernels run
+            const size_t bytes = (size_t)R.n_series * P->ncols * sizeof(double);
+            CK(cudaEventRecord(ctx->ev_peer, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->s_peer, ctx->ev_peer, 0));
+            const size_t np = ctx->peer_out.size();
+            for (size_t k = 1; k < np; ++k) {          // start with the next rank so the ranks do not all hit one peer
+                const size_t p = ((size_t)ctx->peer_self + k) % np;
+                CK(cudaMemcpyAsync((void*)(ctx->peer_out[p] + (uint64_t)peer_off), d_final, bytes, cudaMemcpyDeviceToDevice, ctx->s_peer));
+            }
+        }
     }
     return TSFX_OK;
 }
 
 static int impute_after_extract(tsfx_ctx* ctx, double* d_out, int64_t rows, int cols);
+static int nan_error(tsfx_ctx* ctx);
 
 static int check_args(tsfx_ctx* ctx, const tsfx_plan* plan, const void* values, const void* out, int64_t n_series) {
     if (!ctx) return TSFX_E_INVALID;
@@ -555,11 +760,19 @@ extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const floa
     CK(cudaMemcpyAsync(ctx->begin.p, begin, (size_t)n_series * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->len.p, len, (size_t)n_series * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     R.values = (const float*)ctx->values.p; R.begin = (const int64_t*)ctx->begin.p; R.len = (const int32_t*)ctx->len.p;
+    const bool check_nan = !(flags & TSFX_FLAG_NO_NAN_CHECK);
+    if (check_nan) {
+        CK(ctx->csr.init_info());
+        CK(cudaMemsetAsync(ctx->csr.d_info, 0, sizeof(CsrInfo), ctx->stream));
+        csr_check_nan(ctx->csr, R.values, n_values, ctx->stream);
+        CK(cudaMemcpyAsync(ctx->csr.h_info, ctx->csr.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
     if (rc) return rc;
     if (flags & TSFX_FLAG_IMPUTE) { rc = impute_after_extract(ctx, (double*)ctx->out.p, n_series, plan->ncols); if (rc) return rc; }
     CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (check_nan && ctx->csr.h_info->has_nan) return nan_error(ctx);
     return TSFX_OK;
 }
 
@@ -588,14 +801,16 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
     if (flags & TSFX_FLAG_TIMING) block = n_series;            // per-group events describe one whole pass
     float* dv = (float*)ctx->values.p;
     double* dout = (double*)ctx->out.p;
+    const bool check_nan = !(flags & TSFX_FLAG_NO_NAN_CHECK);
+    if (check_nan) { CK(ctx->csr.init_info()); CK(cudaMemsetAsync(ctx->csr.d_info, 0, sizeof(CsrInfo), ctx->stream)); }
     int nb = 0;
     for (int64_t lo = 0; lo < n_series; lo += block, ++nb) {
         const int64_t cnt = std::min<int64_t>(block, n_series - lo);
         const int slot = nb & 1;
-        CK(cudaMemcpyAsync(dv + (size_t)lo * len, values + (size_t)lo * len, (size_t)cnt * len * sizeof(float),
-                           cudaMemcpyHostToDevice, ctx->s_in));
+        CK(ctx->stager.h2d(dv + (size_t)lo * len, values + (size_t)lo * len, (size_t)cnt * len * sizeof(float), ctx->s_in));
         CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        if (check_nan) csr_check_nan(ctx->csr, dv + (size_t)lo * len, cnt * len, ctx->stream);
         R.values = dv + (size_t)lo * len;
         R.n_series = cnt;
         rc = run_groups(ctx, plan, R, len, dout + (size_t)lo * ncols, flags);
@@ -611,8 +826,10 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
         if (rc) return rc;
         CK(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (check_nan) CK(cudaMemcpyAsync(ctx->csr.h_info, ctx->csr.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (check_nan && ctx->csr.h_info->has_nan) return nan_error(ctx);
     return TSFX_OK;
 }
 
@@ -678,6 +895,69 @@ extern "C" int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names
 extern "C" int tsfx_last_launch_count(const tsfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------ stage (a)
+// Long frame -> device CSR -> kernels, pipelined.  See tsfx_csr.h for the two paths.  `in` columns are host pointers
+// (copied through Stager::h2d: pinned sources go straight to cudaMemcpyAsync, pageable ones through the pinned ring)
+// or, with TSFX_FLAG_DEVICE_PTRS, device pointers that are used in place.
+struct LongIn {
+    const int64_t* ids;
+    const void* keys;
+    int is_f64;
+    const float* values;
+    int64_t n;
+    bool device;
+};
+
+static int nan_error(tsfx_ctx* ctx) { return fail(ctx, TSFX_E_NAN, "the value column contains NaN"); }
+
+// Brings the frame into CSR form on the device (sizes in *info).  When the rows arrive ordered and the input is on
+// the host, only the id column has been copied on return (*streamed = true): the caller streams the other columns.
+static int stage_a(tsfx_ctx* ctx, const LongIn& in, int max_blocks, bool check_nan, CsrInfo* info, bool* streamed,
+                   const int64_t** d_ids_out, const uint64_t** d_keys_out, const float** d_vals_out) {
+    CsrWorkspace& W = ctx->csr;
+    std::string msg;
+    const int64_t n = in.n;
+    const int64_t* d_ids = in.ids;
+    const uint64_t* d_keys = (const uint64_t*)in.keys;
+    const float* d_vals = in.values;
+    if (!in.device) {
+        CK(W.reserve(0, (size_t)n * 8));
+        CK(W.reserve(2, (size_t)n * 4 + 16));
+        if (in.keys) CK(W.reserve(1, (size_t)n * 8));
+        CK(ctx->stager.h2d(W.ids(), in.ids, (size_t)n * 8, ctx->stream));
+        d_ids = W.ids();
+        d_keys = in.keys ? W.keys() : nullptr;
+        d_vals = W.vals();
+    }
+    int rc = csr_ids_pass(W, d_ids, n, 16384, max_blocks, ctx->stream, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    CK(cudaStreamSynchronize(ctx->stream));
+    *info = *W.h_info;
+    *streamed = false;
+    if (!info->unsorted_ids) {
+        W.d_values = const_cast<float*>(d_vals);
+        if (!in.device) *streamed = true;
+        else csr_check_rows(W, d_ids, d_keys, in.is_f64, d_vals, 0, n, check_nan, ctx->stream);   // result read by the caller
+    }
+    *d_ids_out = d_ids; *d_keys_out = d_keys; *d_vals_out = d_vals;
+    return TSFX_OK;
+}
+
+// rows in arbitrary order: (copy the remaining columns,) sort, rebuild the CSR
+static int stage_a_sort(tsfx_ctx* ctx, const LongIn& in, int max_blocks, bool check_nan, CsrInfo* info,
+                        const int64_t* d_ids, const uint64_t* d_keys, const float* d_vals) {
+    CsrWorkspace& W = ctx->csr;
+    std::string msg;
+    if (!in.device) {
+        if (in.keys) CK(ctx->stager.h2d(W.keys(), in.keys, (size_t)in.n * 8, ctx->stream));
+        CK(ctx->stager.h2d(W.vals(), in.values, (size_t)in.n * 4, ctx->stream));
+    }
+    int rc = csr_sort_pass(W, d_ids, d_keys, in.is_f64, d_vals, in.n, 16384, max_blocks, check_nan, ctx->stream, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    CK(cudaStreamSynchronize(ctx->stream));
+    *info = *W.h_info;
+    return TSFX_OK;
+}
+
 extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sort_keys, int32_t sort_key_is_f64,
                               const float* values, int64_t n_rows, int64_t* out_ids, int64_t* out_begin,
                               int32_t* out_len, float* sorted_values, int64_t out_capacity, int64_t* n_series_out) {
@@ -687,20 +967,149 @@ extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sor
     CK(cudaSetDevice(ctx->device));
     *n_series_out = 0;
     if (n_rows == 0) return TSFX_OK;
-    std::string msg;
-    int64_t ns = 0;
     ctx->held_series = -1;
-    int rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
-    if (rc) return fail(ctx, rc, msg);
+    LongIn in{ids, sort_keys, sort_key_is_f64, values, n_rows, false};
+    CsrInfo info;
+    bool streamed = false;
+    const int64_t* d_ids; const uint64_t* d_keys; const float* d_vals;
+    int rc = stage_a(ctx, in, 1, true, &info, &streamed, &d_ids, &d_keys, &d_vals);
+    if (rc) return rc;
+    CsrWorkspace& W = ctx->csr;
+    bool need_sort = info.unsorted_ids != 0;
+    if (!need_sort) {        // ids ascending: bring the other columns over and look inside the ids
+        if (sort_keys) CK(ctx->stager.h2d(W.keys(), sort_keys, (size_t)n_rows * 8, ctx->stream));
+        CK(ctx->stager.h2d(W.vals(), values, (size_t)n_rows * 4, ctx->stream));
+        csr_check_rows(W, d_ids, d_keys, sort_key_is_f64, d_vals, 0, n_rows, true, ctx->stream);
+        CK(cudaMemcpyAsync(W.h_info, W.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        info = *W.h_info;
+        need_sort = info.unsorted_keys != 0;
+        if (need_sort) {     // columns are resident now: sort in place
+            LongIn dev{d_ids, d_keys, sort_key_is_f64, d_vals, n_rows, true};
+            rc = stage_a_sort(ctx, dev, 1, true, &info, d_ids, d_keys, d_vals);
+            if (rc) return rc;
+        }
+    } else {
+        rc = stage_a_sort(ctx, in, 1, true, &info, d_ids, d_keys, d_vals);
+        if (rc) return rc;
+    }
+    if (info.has_nan) return nan_error(ctx);
+    const int64_t ns = info.n_series;
     ctx->held_series = ns;
+    ctx->held_max_len = info.max_len;
     *n_series_out = ns;
     if (!out_ids && !out_begin && !out_len && !sorted_values) return TSFX_OK;      // count + keep on device
     if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
-    if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_begin) CK(cudaMemcpyAsync(out_begin, ctx->csr.d_begin, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_len) CK(cudaMemcpyAsync(out_len, ctx->csr.d_len, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (sorted_values) CK(cudaMemcpyAsync(sorted_values, ctx->csr.d_values, n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ids) CK(cudaMemcpyAsync(out_ids, W.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_begin) CK(cudaMemcpyAsync(out_begin, W.d_begin, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_len) CK(cudaMemcpyAsync(out_len, W.d_len, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sorted_values) CK(cudaMemcpyAsync(sorted_values, W.d_values, n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return TSFX_OK;
+}
+
+// kernels + result transfer over the row blocks of a device CSR.  stream_in: the key / value rows of a block are
+// copied from the host right before the block's kernels (fast path); d_out == nullptr: results go through ctx->out
+// and are copied to `out` (host) block by block on the D2H stream.
+static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info, const LongIn* stream_in,
+                      const int64_t* d_ids, const uint64_t* d_keys, const float* d_vals, bool check_rows, bool check_nan,
+                      double* out, bool out_is_device, uint32_t flags) {
+    CsrWorkspace& W = ctx->csr;
+    const size_t ncols = (size_t)plan->ncols;
+    const int64_t ns = info.n_series;
+    double* dout = out;
+    if (!out_is_device) {
+        CK(ctx->out.reserve(std::max<size_t>((size_t)ns * ncols * sizeof(double), 8)));
+        dout = (double*)ctx->out.p;
+    }
+    const bool impute = (flags & TSFX_FLAG_IMPUTE) != 0;
+    for (int b = 0; b < info.n_blocks; ++b) {
+        const int64_t s0 = info.series_lo[b], s1 = info.series_lo[b + 1];
+        const int64_t r0 = info.row_lo[b], r1 = info.row_lo[b + 1];
+        const int slot = b & 1;
+        if (stream_in) {
+            if (stream_in->keys) CK(ctx->stager.h2d(W.keys() + r0, (const uint64_t*)stream_in->keys + r0, (size_t)(r1 - r0) * 8, ctx->s_in));
+            CK(ctx->stager.h2d(W.vals() + r0, stream_in->values + r0, (size_t)(r1 - r0) * 4, ctx->s_in));
+            CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        }
+        if (check_rows) csr_check_rows(W, d_ids, d_keys, stream_in ? stream_in->is_f64 : 0, d_vals, r0, r1, check_nan, ctx->stream);
+        SeriesRef R;
+        R.values = W.d_values; R.begin = W.d_begin + s0; R.len = W.d_len + s0; R.dense_len = 0; R.n_series = s1 - s0;
+        int rc = run_groups(ctx, plan, R, info.max_len, dout + (size_t)s0 * ncols, flags);
+        if (rc) return rc;
+        if (impute || out_is_device) continue;
+        CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0));
+        CK(cudaMemcpyAsync(out + (size_t)s0 * ncols, dout + (size_t)s0 * ncols, (size_t)(s1 - s0) * ncols * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    if (impute) {
+        int rc = impute_after_extract(ctx, dout, ns, plan->ncols);
+        if (rc) return rc;
+        if (!out_is_device) CK(cudaMemcpyAsync(out, dout, (size_t)ns * ncols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return TSFX_OK;
+}
+
+static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn& in, int64_t* out_ids, double* out,
+                             int64_t out_capacity, int64_t** out_ids_alloc, double** out_alloc, int64_t* n_series_out,
+                             uint32_t flags) {
+    CsrWorkspace& W = ctx->csr;
+    const bool check_nan = !(flags & TSFX_FLAG_NO_NAN_CHECK);
+    const int max_blocks = (flags & TSFX_FLAG_TIMING) ? 1 : 16;
+    ctx->held_series = -1;
+    CsrInfo info;
+    bool streamed = false;
+    const int64_t* d_ids; const uint64_t* d_keys; const float* d_vals;
+    int rc = stage_a(ctx, in, max_blocks, check_nan, &info, &streamed, &d_ids, &d_keys, &d_vals);
+    if (rc) return rc;
+    bool sorted = !info.unsorted_ids;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!sorted) {
+            rc = stage_a_sort(ctx, in, max_blocks, check_nan, &info, d_ids, d_keys, d_vals);
+            if (rc) return rc;
+            if (info.has_nan) return nan_error(ctx);
+        }
+        const int64_t ns = info.n_series;
+        *n_series_out = ns;
+        const size_t ob = (size_t)ns * plan->ncols * sizeof(double);
+        if (out_alloc) {                         // library-sized result from the pinned pool
+            if (!*out_alloc) {
+                *out_alloc = (double*)ctx->pool.alloc(std::max<size_t>(ob, 8));
+                *out_ids_alloc = (int64_t*)ctx->pool.alloc(std::max<size_t>((size_t)ns * 8, 8));
+                if (!*out_alloc || !*out_ids_alloc) return fail(ctx, TSFX_E_NOMEM, "pinned host allocation failed");
+            }
+            out = *out_alloc;
+            out_ids = *out_ids_alloc;
+        } else if (ns > out_capacity) {
+            return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
+        }
+        if (info.max_len < 1 && ns > 0) return fail(ctx, TSFX_E_INVALID, "empty series");
+        const bool first_sorted_try = sorted && attempt == 0;
+        rc = run_blocks(ctx, plan, info, (first_sorted_try && streamed) ? &in : nullptr, d_ids, d_keys, d_vals,
+                        /*check_rows=*/first_sorted_try && streamed, check_nan, out, in.device, flags);
+        if (rc) return rc;
+        if (out_ids) CK(cudaMemcpyAsync(out_ids, W.d_uid, (size_t)ns * sizeof(int64_t), in.device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        if (in.device && !first_sorted_try) break;                       // asynchronous contract: nothing to wait for
+        if (first_sorted_try) CK(cudaMemcpyAsync(W.h_info, W.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->s_out));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!first_sorted_try) break;
+        if (W.h_info->has_nan) return nan_error(ctx);
+        if (!W.h_info->unsorted_keys) break;
+        // ids ascending but some sort key decreases inside an id: the columns are resident now, sort and run again
+        sorted = false;
+        if (!in.device) {
+            LongIn dev{d_ids, d_keys, in.is_f64, d_vals, in.n, true};
+            rc = stage_a_sort(ctx, dev, max_blocks, check_nan, &info, d_ids, d_keys, d_vals);
+            if (rc) return rc;
+            sorted = true;                        // CSR rebuilt: second trip only runs the kernels
+            streamed = false;
+        }
+    }
+    ctx->held_series = info.n_series;
+    ctx->held_max_len = info.max_len;
     return TSFX_OK;
 }
 
@@ -709,40 +1118,91 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
                                  double* out, int64_t out_capacity, int64_t* n_series_out, uint32_t flags) {
     if (!ctx) return TSFX_E_INVALID;
     if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
-    if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long takes host pointers");
     const bool reuse = (ids == nullptr && values == nullptr);     // run on the CSR held from tsfx_build_csr
     if (n_rows < 0 || !n_series_out || (!reuse && n_rows > 0 && (!ids || !values)) || !out)
         return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: bad arguments");
     CK(cudaSetDevice(ctx->device));
     *n_series_out = 0;
-    std::string msg;
-    int64_t ns = 0;
-    int rc;
     if (reuse) {
+        if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "the held CSR is extracted into host buffers");
         if (ctx->held_series < 0) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: no CSR is held by this context");
-        ns = ctx->held_series;
-    } else {
-        if (n_rows == 0) return TSFX_OK;
-        ctx->held_series = -1;
-        rc = csr_build_from_host(ctx->csr, ids, sort_keys, sort_key_is_f64, values, n_rows, ctx->stream, &ns, &msg);
-        if (rc) return fail(ctx, rc, msg);
-        ctx->held_series = ns;
+        const int64_t ns = ctx->held_series;
+        *n_series_out = ns;
+        if (ns == 0) return TSFX_OK;
+        if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
+        CsrInfo info = {};
+        info.n_series = ns; info.max_len = ctx->held_max_len; info.n_blocks = 1;
+        info.series_lo[0] = 0; info.series_lo[1] = ns; info.row_lo[0] = 0; info.row_lo[1] = 0;
+        int rc = run_blocks(ctx, plan, info, nullptr, nullptr, nullptr, nullptr, false, false, out, false, flags);
+        if (rc) return rc;
+        if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->s_out));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return TSFX_OK;
     }
-    *n_series_out = ns;
-    if (ns == 0) return TSFX_OK;
-    if (ns > out_capacity) return fail(ctx, TSFX_E_INVALID, "out_capacity too small: " + std::to_string(ns) + " series");
-    int max_len = 0;
-    if (csr_max_len(ctx->csr, ctx->csr.d_len, ns, ctx->stream, &max_len)) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
-    size_t ob = (size_t)ns * plan->ncols * sizeof(double);
-    CK(ctx->out.reserve(std::max<size_t>(ob, 8)));
-    SeriesRef R;
-    R.values = ctx->csr.d_values; R.begin = ctx->csr.d_begin; R.len = ctx->csr.d_len; R.dense_len = 0; R.n_series = ns;
-    rc = run_groups(ctx, plan, R, max_len, (double*)ctx->out.p, flags);
-    if (rc) return rc;
-    if (flags & TSFX_FLAG_IMPUTE) { rc = impute_after_extract(ctx, (double*)ctx->out.p, ns, plan->ncols); if (rc) return rc; }
-    if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(out, ctx->out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_rows == 0) return TSFX_OK;
+    LongIn in{ids, sort_keys, sort_key_is_f64, values, n_rows, (flags & TSFX_FLAG_DEVICE_PTRS) != 0};
+    return extract_long_impl(ctx, plan, in, out_ids, out, out_capacity, nullptr, nullptr, n_series_out, flags);
+}
+
+extern "C" int tsfx_extract_long_alloc(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
+                                       int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t** out_ids,
+                                       double** out, int64_t* n_series_out, uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (!plan || plan->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
+    if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long_alloc takes host pointers");
+    if (n_rows < 0 || !n_series_out || !out || !out_ids || (n_rows > 0 && (!ids || !values)))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long_alloc: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    *n_series_out = 0;
+    *out = nullptr;
+    *out_ids = nullptr;
+    if (n_rows == 0) return TSFX_OK;
+    LongIn in{ids, sort_keys, sort_key_is_f64, values, n_rows, false};
+    int rc = extract_long_impl(ctx, plan, in, nullptr, nullptr, 0, out_ids, out, n_series_out, flags);
+    if (rc) {
+        if (*out) ctx->pool.free(*out);
+        if (*out_ids) ctx->pool.free(*out_ids);
+        *out = nullptr; *out_ids = nullptr;
+    }
+    return rc;
+}
+
+extern "C" void* tsfx_host_alloc(tsfx_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    return ctx->pool.alloc(bytes);
+}
+extern "C" void tsfx_host_free(tsfx_ctx* ctx, void* p) {
+    if (ctx && p) ctx->pool.free(p);
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU placement
+extern "C" int tsfx_set_peer_outputs(tsfx_ctx* ctx, const uint64_t* peer_out, int32_t n_peers, int32_t self_index,
+                                     uint64_t multicast_out, int32_t mode) {
+    if (!ctx) return TSFX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_peer));
+    ctx->peer_out.clear();
+    ctx->peer_self = -1;
+    ctx->peer_mc = 0;
+    if (n_peers <= 0) return TSFX_OK;
+    if (!peer_out || self_index < 0 || self_index >= n_peers || n_peers > 8 || mode < TSFX_PEER_AUTO || mode > TSFX_PEER_MULTICAST)
+        return fail(ctx, TSFX_E_INVALID, "tsfx_set_peer_outputs: bad arguments (at most 8 ranks)");
+    if (mode == TSFX_PEER_AUTO) mode = multicast_out ? TSFX_PEER_MULTICAST : TSFX_PEER_COPY;
+    if (mode == TSFX_PEER_MULTICAST && !multicast_out) return fail(ctx, TSFX_E_INVALID, "no multicast mapping was supplied");
+    ctx->peer_out.assign(peer_out, peer_out + n_peers);
+    ctx->peer_self = self_index;
+    ctx->peer_mc = multicast_out;
+    ctx->peer_mode = mode;
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_peer_flush(tsfx_ctx* ctx) {
+    if (!ctx) return TSFX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_peer, ctx->s_peer));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_peer, 0));
     return TSFX_OK;
 }
 

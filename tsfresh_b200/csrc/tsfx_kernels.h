@@ -87,6 +87,12 @@ struct AssembleArgs {
     int n_groups;
     int cum[G_COUNT + 1];         // columns before group g (cum[n_groups] = total staged columns)
     const int32_t* final_col;     // device: final column of staged column (cum[g] + j)
+    // multi-GPU result placement (tsfx_set_peer_outputs): the finished row is ALSO stored at the same offset of
+    // every peer's mapped result matrix (plain P2P stores over NVLink), or -- when the result matrix has a multicast
+    // mapping -- stored once through it (the NVSwitch replicates the store to every GPU, including this one)
+    int n_extra;
+    double* extra[7];
+    double* out_mc;               // non-null: store through the multicast mapping instead of `out`
 };
 cudaError_t launch_assemble(const AssembleArgs& A, cudaStream_t st, int sm_count);
 

@@ -27,6 +27,11 @@ from .settings import ComprehensiveFCParameters
 _ctx_lock = threading.Lock()
 _contexts = {}
 
+# the reference's default for n_jobs (tsfresh/defaults.py: N_PROCESSES = max(1, cpu_count // 2)); here n_jobs caps the
+# number of GPUs one process drives (see extract_features)
+import os as _os
+N_PROCESSES = max(1, (_os.cpu_count() or 2) // 2)
+
 
 def get_context(device=None):
     """The process-wide tsfx context for `device` (default: LOCAL_RANK or 0)."""
@@ -57,10 +62,20 @@ def _check_colname(*columns):
             raise ValueError("Dict keys are not allowed to contain '__': {}".format(col))
 
 
-def _check_nan(df, *columns):
+_HOST_NAN_CHECK_ROWS = 1 << 20      # larger float value columns are scanned on the device instead of by pandas
+
+
+def _check_nan(df, *columns, on_device=()):
+    """data.py:148-167.  Integer / bool columns cannot hold NaN (no pass over the data); float VALUE columns named in
+    `on_device` are scanned by the library while they are on the GPU (TSFX_E_NAN -> the same ValueError)."""
     for col in columns:
         if col not in df.columns:
             raise ValueError("Column not found: {}".format(col))
+        kind = getattr(df[col].dtype, "kind", "O")
+        if kind in "iub":
+            continue
+        if col in on_device and kind == "f" and len(df) > _HOST_NAN_CHECK_ROWS:
+            continue
         if df[col].isnull().any():
             raise ValueError("Column must not contain NaN values: {}".format(col))
 
@@ -89,7 +104,9 @@ def _sort_keys(col):
 
 def _frames(container, column_id, column_kind, column_value, column_sort):
     """Normalises the supported input formats (data.py:447-500) to a list of
-    (kind, id column, sort keys or None, float32 values, has_datetime_index)."""
+    (kind, id column, sort keys or None, float32 values, has_datetime_index).  `kind` is the RAW column label / dict
+    key / kind value: the reference looks it up in kind_to_fc_parameters as is (extraction.py:333-336) and only
+    stringifies it for the feature names (:374-378)."""
     out = []
     if isinstance(container, pd.DataFrame):
         df = container
@@ -104,33 +121,33 @@ def _frames(container, column_id, column_kind, column_value, column_sort):
                         f"These columns where currently unused: {','.join(poss)}"
                         "Please hand it to the function as an argument.")
                 column_value = poss[0]
-            _check_nan(df, column_id, column_kind, column_value)
+            _check_nan(df, column_id, column_kind, column_value, on_device=(column_value,))
             if column_sort is not None:
                 _check_nan(df, column_sort)
             for kind, sub in df.groupby(column_kind, sort=True):
-                out.append((str(kind), sub[column_id], sub[column_sort] if column_sort is not None else None,
+                out.append((kind, sub[column_id], sub[column_sort] if column_sort is not None else None,
                             sub[column_value], isinstance(sub.index, pd.DatetimeIndex)))
             id_dtype = df[column_id].dtype
         else:                                                        # wide format (data.py:181-230)
             _check_nan(df, column_id)
             value_columns = [column_value] if column_value is not None else _value_columns(df, column_id, column_sort)
-            _check_nan(df, *value_columns)
+            _check_nan(df, *value_columns, on_device=tuple(value_columns))
             _check_colname(*value_columns)
             if column_sort is not None:
                 _check_nan(df, column_sort)
             for kind in value_columns:
-                out.append((str(kind), df[column_id], df[column_sort] if column_sort is not None else None, df[kind],
+                out.append((kind, df[column_id], df[column_sort] if column_sort is not None else None, df[kind],
                             isinstance(df.index, pd.DatetimeIndex)))
             id_dtype = df[column_id].dtype
     elif isinstance(container, dict):                                # dict of frames (data.py:294-338)
         _check_colname(*list(container.keys()))
         id_dtype = None
         for df in container.values():
-            _check_nan(df, column_id, column_value)
+            _check_nan(df, column_id, column_value, on_device=(column_value,))
         for kind, df in container.items():
             if column_sort is not None:
                 _check_nan(df, column_sort)
-            out.append((str(kind), df[column_id], df[column_sort] if column_sort is not None else None,
+            out.append((kind, df[column_id], df[column_sort] if column_sort is not None else None,
                         df[column_value], isinstance(df.index, pd.DatetimeIndex)))
             id_dtype = df[column_id].dtype
     else:
@@ -166,7 +183,12 @@ def _extract_rolled(rolled, default_fc_parameters, kind_to_fc_parameters, impute
         names = [kind + "__" + s for s in plan.suffixes]
         if plan.n_cols == 0 or len(begin) == 0:
             return names, np.empty((len(begin), plan.n_cols))
-        return names, _device_plan(ctx, plan).extract_csr(values, begin, length, flags=flags)
+        try:
+            return names, _device_plan(ctx, plan).extract_csr(values, begin, length, flags=flags)
+        except ValueError as e:
+            if "contains NaN" in str(e):      # the reference raises this while adapting the rolled frame (data.py:148-167)
+                raise ValueError("Column must not contain NaN values: {}".format(kind)) from None
+            raise
 
     if rolled.parts is None:                 # wide frame: every kind shares the windows
         flags = _lib.FLAG_IMPUTE if device_impute else 0          # columns are independent: per-kind impute is exact
@@ -208,7 +230,7 @@ def _extract_rolled(rolled, default_fc_parameters, kind_to_fc_parameters, impute
 
 
 def extract_features(timeseries_container, default_fc_parameters=None, kind_to_fc_parameters=None, column_id=None,
-                     column_sort=None, column_kind=None, column_value=None, chunksize=None, n_jobs=1,
+                     column_sort=None, column_kind=None, column_value=None, chunksize=None, n_jobs=N_PROCESSES,
                      show_warnings=False, disable_progressbar=False, impute_function=None, profile=False,
                      profiling_filename="profile.txt", profiling_sorting="cumulative", distributor=None, pivot=True,
                      device=None):
@@ -242,6 +264,8 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             fc = kind_to_fc_parameters[kind]
         else:
             fc = default_fc_parameters
+        value_name = values.name
+        kind = str(kind)
         plan = Plan(fc, has_datetime_index=has_dt)
         for name in plan.skipped:
             if show_warnings:
@@ -254,7 +278,12 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             continue
         dp = _device_plan(ctx, plan)
         v32 = values.to_numpy().astype(np.float32, copy=False)
-        uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags)
+        try:
+            uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags)
+        except ValueError as e:
+            if "contains NaN" in str(e):          # TSFX_E_NAN: the check of data.py:148-167, done on the device
+                raise ValueError("Column must not contain NaN values: {}".format(value_name)) from None
+            raise
         blocks.append((names, uid, mat))
 
     # ---- assemble (PartitionedTsData.pivot, data.py:86-121): union of ids, sorted, id dtype restored

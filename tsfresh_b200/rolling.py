@@ -147,6 +147,13 @@ def _roll_frame(df, column_id, column_sort, rolling_direction, max_timeshift, mi
         v = df[c].to_numpy()
         values[str(c)] = np.ascontiguousarray(v if order is None else v[order], dtype=np.float32)
     row_of_id = begin[wp] + we
-    names = sort_col[row_of_id] if sort_col is not None else we
-    ids = list(zip(uid[wp].tolist(), np.asarray(names).tolist()))
+    # window names keep their pandas scalar types (Timestamp / Timedelta for datetime-like sort columns, as the
+    # reference's (id, timestamp) tuples do, dataframe_functions.py:365-366); plain numbers go through tolist()
+    if sort_col is None:
+        names = np.asarray(we).tolist()
+    elif sort_col.dtype.kind in "mM":
+        names = list(pd.Index(sort_col[row_of_id]))
+    else:
+        names = np.asarray(sort_col[row_of_id]).tolist()
+    ids = list(zip(uid[wp].tolist(), names))
     return RolledTimeSeries(values, wb, wl, ids, wp, we, sort_col, column_sort)
