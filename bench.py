@@ -171,11 +171,139 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return "%sFCParameters on %d series x len %d per GPU (BASELINE.json configs[2] shape), synthetic N(0,1) float32" % (
-        args.settings.capitalize(), args.series, args.len)
+    tag = ""
+    if (args.settings, args.series, args.len) == ("comprehensive", 1_000_000, 256):
+        tag = " (BASELINE.json configs[2])"
+    elif (args.settings, args.len) == ("comprehensive", 1024):
+        tag = " (BASELINE.json configs[3] shape)"
+    elif (args.settings, args.series, args.len) == ("efficient", 100_000, 256):
+        tag = " (BASELINE.json configs[1])"
+    return "%sFCParameters on %d series x len %d per GPU%s, synthetic N(0,1) float32" % (
+        args.settings.capitalize(), args.series, args.len, tag)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+class Bench:
+    """shared state of the GPU arm: process group, stream, context, timing helpers"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from tsfresh_b200 import _lib
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.saved_stdout = None
+        if self.world > 1:
+            # keep stdout to the single JSON line: NCCL prints its version banner with printf on fd 1 when the first
+            # communicator is created, so fd 1 points at stderr until the result line is written
+            sys.stdout.flush()
+            self.saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=self.dev)
+        # a non-default torch stream shared with the library, so torch's CUDA events bracket the library's launches
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self.ctx = _lib.Context(self.local_rank, stream=self.stream.cuda_stream)
+        self.plans = {}
+
+    def plan(self, name):
+        from tsfresh_b200.plan import Plan
+        if name not in self.plans:
+            p = Plan(settings_by_name(name))
+            self.plans[name] = (p, self._lib.DevicePlan(self.ctx, p))
+        return self.plans[name]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, after_step=None):
+        """W untimed + K timed calls of fn bracketed by barrier + synchronize; CUDA events on the library's stream;
+        returns ms per step, max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+            if after_step:
+                after_step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+            if after_step:
+                after_step()
+        e1.record(self.stream)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    def wall(self, fn, steps, warmup):
+        """host-timed variant for calls that synchronise themselves (host-buffer entry points, the Python API)"""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        t = torch.tensor([dt], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def randn(self, shape, seed):
+        gen = self.torch.Generator(device=self.dev)
+        gen.manual_seed(seed)
+        return self.torch.randn(shape, generator=gen, device=self.dev, dtype=self.torch.float32)
+
+
+def sharded_pass(B, name, values, S, L, steps, warmup, csr=None, placement="auto"):
+    """One configuration, device-resident: every rank extracts its S series (dense [S, L] tensor, or a CSR
+    (begin, length) over `values`) and the rows are placed on every rank (tsfresh_b200.distributed.GatheredMatrix).
+    Returns (ms per step max over ranks, per-group ms of one extra timed pass over this rank's shard, launches/step, gm)."""
+    from tsfresh_b200.distributed import GatheredMatrix, extract_csr_sharded_device, extract_dense_sharded_device
+    torch = B.torch
+    plan, dp = B.plan(name)
+    gm = GatheredMatrix(S, plan.n_cols, B.dev, mode=placement)
+    gm.attach(B.ctx)
+    blocks = [1]
+
+    def step():
+        if csr is None:
+            blocks[0] = extract_dense_sharded_device(dp, values, gm, stream=B.stream, ctx_on_current_stream=True)
+        else:
+            blocks[0] = extract_csr_sharded_device(dp, values, csr[0], csr[1], gm, stream=B.stream, ctx_on_current_stream=True,
+                                                   max_len=L)
+        if B.world > 1:
+            gm.finish(B.ctx, stream=B.stream, ctx_on_current_stream=True)
+
+    ms = B.timed(step, steps, warmup)
+    launches = B.ctx.launch_count() * blocks[0]
+    gm.detach(B.ctx)
+    # per-group CUDA events: one extra pass over this rank's whole shard with TSFX_FLAG_TIMING
+    if csr is None:
+        dp.extract_dense_device(values.data_ptr(), S, L, gm.local_ptr(0), timing=True)
+    else:
+        dp.extract_csr_device(values.data_ptr(), values.numel(), csr[0].data_ptr(), csr[1].data_ptr(), S, gm.local_ptr(0), timing=True,
+                              max_len=L)
+    torch.cuda.synchronize()
+    groups = B.ctx.timings()
+    return ms, groups, launches, gm
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,206 +315,217 @@ def main():
     ap.add_argument("--settings", default="comprehensive", choices=["comprehensive", "efficient", "minimal"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline configuration only")
+    ap.add_argument("--placement", default="auto", choices=["auto", "copy", "store", "multicast", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    from tsfresh_b200 import _lib
-    from tsfresh_b200.plan import Plan
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    saved_stdout = None
-    if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner with printf on fd 1 when the first
-        # communicator is created, so fd 1 points at stderr until the result line is written
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
-
+    B = Bench(args)
+    torch, dist, _lib = B.torch, B.dist, B._lib
+    rank, world = B.rank, B.world
     S, L = args.series, args.len
-    plan = Plan(settings_by_name(args.settings))
+    plan, dp = B.plan(args.settings)
     F = plan.n_cols
-    # a non-default torch stream shared with the library, so torch's CUDA events bracket the library's launches
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
-    dp = _lib.DevicePlan(ctx, plan)
+    peaks, which = measured_peaks()
 
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(42 + 2 + rank)
-    values = torch.randn((S, L), generator=gen, device=dev, dtype=torch.float32)
-    out = torch.empty((S, F), device=dev, dtype=torch.float64)
-    gathered = None
-    comm_stream = None
-    n_blocks = 8
-    if world > 1:
-        gathered = torch.empty((world, S, F), device=dev, dtype=torch.float64)
-        comm_stream = torch.cuda.Stream(device=dev)
-
-    def step(timing=False):
-        if world == 1:
-            dp.extract_dense_device(values.data_ptr(), S, L, out.data_ptr(), timing=timing)
-            return
-        # row blocks: kernels of block b+1 overlap the all-gather of block b (side stream)
-        bs = (S + n_blocks - 1) // n_blocks
-        for b in range(n_blocks):
-            lo, hi = b * bs, min(S, (b + 1) * bs)
-            if lo >= hi:
-                break
-            dp.extract_dense_device(values[lo:hi].data_ptr(), hi - lo, L, out[lo:hi].data_ptr(), timing=False)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                # gathered[r, lo:hi] <- rank r's block; contiguous per rank, so gather into a staging view
-                dist.all_gather_into_tensor(gathered_stage[b][: world * (hi - lo) * F], out[lo:hi].reshape(-1))
-        stream.wait_stream(comm_stream)
-
-    gathered_stage = None
-    if world > 1:
-        bs = (S + n_blocks - 1) // n_blocks
-        gathered_stage = [torch.empty(world * bs * F, device=dev, dtype=torch.float64) for _ in range(n_blocks)]
-        del gathered
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    multi_stream = int(os.environ.get("TSFX_STREAMS", "1")) > 1      # groups overlap: per-group events need a separate pass
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    # ---------------- headline: BASELINE.json configs[2] shape per GPU (weak scaling), device resident
+    values = B.randn((S, L), 42 + 2 + rank)
+    sampler = ClockSampler(B.local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    group_ms = {}
-    e0.record(stream)
-    for _ in range(args.steps):
-        step(timing=(world == 1 and not multi_stream))
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    # per-group CUDA events: taken from the last timed step at N=1, from one extra (untimed) pass over this rank's
-    # shard at N>1 (the timed steps there are split into row blocks for the all-gather overlap)
-    if world > 1 or multi_stream:
-        dp.extract_dense_device(values.data_ptr(), S, L, out.data_ptr(), timing=True)
-        torch.cuda.synchronize()
-    group_ms = ctx.timings()
+    ms_step, group_ms, launches_per_step, gm = sharded_pass(B, args.settings, values, S, L, args.steps, args.warmup,
+                                                           placement=args.placement)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     value = world * S / (ms_step / 1e3)
-    launches_per_step = ctx.launch_count() * (1 if world == 1 else n_blocks)
-    if rank != 0:
-        group_ms = {}
+    placement = gm.placement()
 
-    # ---------------- impute of the resident feature matrix: the HBM-bound pass of the framework
+    # ---------------- impute of the resident feature matrix: an HBM-bound pass of the framework
     impute_info = None
     if world == 1:
-        ctx.impute_device(out.data_ptr(), S, F)                     # warm-up (allocations)
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record(stream)
-        for _ in range(3):
-            ctx.impute_device(out.data_ptr(), S, F)
-        i1.record(stream)
-        torch.cuda.synchronize()
-        ims = i0.elapsed_time(i1) / 3
+        out_ptr = gm.local_ptr(0)
+        B.ctx.impute_device(out_ptr, S, F)                     # warm-up (allocations)
+        ims = B.timed(lambda: B.ctx.impute_device(out_ptr, S, F), 3, 0)
         # algorithmic bytes: the statistics sweep reads the matrix once; the replacement sweep only visits the
         # (row slice, column tile) blocks that hold a non-finite value
         impute_info = {"ms": ims, "algorithmic_GB": S * F * 8 / 1e9, "GBps": S * F * 8 / (ims * 1e-3) / 1e9,
                        "bound": "hbm", "kernels": "k_col_stats + k_col_reduce + k_impute_apply (+ one radix sort per NaN column)"}
+    del gm
+    torch.cuda.empty_cache()
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
-    e2e = None
+    e2e = e2e_long = e2e_api = None
+    n_e2e = max(2, min(args.steps, 4))
     if not args.no_e2e:
         hv = torch.empty((S, L), dtype=torch.float32).pin_memory()
         hv.copy_(values.cpu())
         ho = torch.empty((S, F), dtype=torch.float64).pin_memory()
         hv_np, ho_np = hv.numpy(), ho.numpy()
-        del out
-        torch.cuda.empty_cache()
-        for _ in range(2):
-            dp.extract_dense(hv_np, out=ho_np)
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(2, min(args.steps, 5))
-        for _ in range(n_e2e):
-            dp.extract_dense(hv_np, out=ho_np)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = B.wall(lambda: dp.extract_dense(hv_np, out=ho_np), n_e2e, 2)
         e2e = {"value": world * S / dt, "unit": "series/s", "h2d_bytes_per_step": int(S * L * 4),
                "d2h_bytes_per_step": int(S * F * 8), "ms_per_step": dt * 1e3,
                "call": "tsfx_extract_dense (C ABI, pinned host buffers)"}
+        del ho, ho_np
+        if world == 1 and not args.no_configs:
+            # ---- the north-star boundary: a long (id, time, value) frame, 20 bytes per row, rows ordered by (id, time)
+            ids = B.ctx.pinned_array((S * L,), np.int64)
+            tms = B.ctx.pinned_array((S * L,), np.int64)
+            ids.reshape(S, L)[:] = np.arange(S, dtype=np.int64)[:, None]
+            tms.reshape(S, L)[:] = np.arange(L, dtype=np.int64)[None, :]
+            vflat = hv_np.reshape(-1)
 
+            def long_call():
+                uid, mat = dp.extract_long(ids, tms, vflat)
+                assert mat.shape == (S, F)
+            dt = B.wall(long_call, n_e2e, 1)
+            e2e_long = {"value": S / dt, "unit": "series/s", "ms_per_step": dt * 1e3,
+                        "h2d_bytes_per_step": int(S * L * 20), "d2h_bytes_per_step": int(S * F * 8 + S * 8),
+                        "call": "tsfx_extract_long_alloc (C ABI): pinned (id int64, time int64, value float32) columns of "
+                                "%d rows in (id, time) order -> device CSR -> kernels -> pinned result" % (S * L)}
+            # ---- the user-facing call: tsfresh_b200.extract_features(DataFrame) on pageable pandas columns
+            import pandas as pd
+            from tsfresh_b200 import extract_features
+            df = pd.DataFrame({"id": np.array(ids), "time": np.array(tms), "value": np.array(vflat)})
+            del ids, tms
+            fc = settings_by_name(args.settings)
+
+            def api_call():
+                X = extract_features(df, column_id="id", column_sort="time", default_fc_parameters=fc,
+                                     disable_progressbar=True, device=B.local_rank, n_jobs=1)
+                assert X.shape == (S, F)
+            dt = B.wall(api_call, max(2, n_e2e - 1), 1)
+            e2e_api = {"value": S / dt, "unit": "series/s", "ms_per_step": dt * 1e3,
+                       "h2d_bytes_per_step": int(S * L * 20), "d2h_bytes_per_step": int(S * F * 8 + S * 8),
+                       "call": "tsfresh_b200.extract_features(pandas.DataFrame of %d rows, column_id, column_sort) -> DataFrame "
+                               "[%d x %d]" % (S * L, S, F)}
+            del df
+        del hv, hv_np
+    del values
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE configurations, same JSON line
+    configs = {}
+    if not args.no_configs and args.settings == "comprehensive" and (S, L) == (1_000_000, 256):
+        ksteps, kwarm = max(2, min(args.steps, 3)), 1
+
+        def entry(name, workload, S_rank, L_, ms, groups, scaling, extra=None):
+            pl, _ = B.plan(name)
+            tot = world * S_rank if scaling == "weak" else None
+            d = {"workload": workload, "ms_per_step": ms, "scaling": scaling, "columns": pl.n_cols,
+                 "groups_ms": groups}
+            if extra:
+                d.update(extra)
+            return d
+
+        # config 2: EfficientFCParameters, 100 000 x 256 (a single-GPU configuration: N = 1 only)
+        if world == 1:
+            v2 = B.randn((100_000, 256), 42 + 1)
+            ms2, g2, _, gm2 = sharded_pass(B, "efficient", v2, 100_000, 256, ksteps + 2, 2)
+            configs["config2"] = entry("efficient", "EfficientFCParameters on 100 000 series x len 256, 1 GPU (BASELINE.json configs[1])",
+                                       100_000, 256, ms2, g2, "n/a", {"value": 100_000 / (ms2 / 1e3), "unit": "series/s"})
+            del gm2
+            try:
+                import pandas as pd
+                from tsfresh_b200 import extract_features
+                h2 = v2.cpu().numpy()
+                df2 = pd.DataFrame({"id": np.repeat(np.arange(100_000, dtype=np.int64), 256),
+                                    "time": np.tile(np.arange(256, dtype=np.int64), 100_000), "value": h2.reshape(-1)})
+                fc2 = settings_by_name("efficient")
+                dt2 = B.wall(lambda: extract_features(df2, column_id="id", column_sort="time", default_fc_parameters=fc2,
+                                                      disable_progressbar=True, device=B.local_rank, n_jobs=1), 3, 1)
+                configs["config2"]["e2e_api"] = {"value": 100_000 / dt2, "unit": "series/s", "ms_per_step": dt2 * 1e3,
+                                                 "call": "tsfresh_b200.extract_features(DataFrame of 25.6 M rows)"}
+                del df2, h2
+            except Exception as e:                        # the bench line must survive a host-side failure here
+                configs["config2"]["e2e_api"] = {"error": repr(e)}
+            del v2
+            torch.cuda.empty_cache()
+            # reduction-only plan (class M of SURVEY 8a): the kernel the north star's HBM target is stated for
+            vm = B.randn((S, L), 42 + 9)
+            msm, gmn, _, gmm = sharded_pass(B, "minimal", vm, S, L, ksteps + 2, 2)
+            plm, _ = B.plan("minimal")
+            configs["minimal"] = entry("minimal", "MinimalFCParameters on 1 000 000 series x len 256 (class-M reductions + median)",
+                                       S, L, msm, gmn, "n/a", {"value": S / (msm / 1e3), "unit": "series/s"})
+            del vm, gmm
+            torch.cuda.empty_cache()
+
+        # config 4: ComprehensiveFCParameters, 1 000 000 x 1024 in total, STRONG scaling: each rank takes 1 M / N series
+        S4 = 1_000_000 // world
+        v4 = B.randn((S4, 1024), 42 + 3 + 17 * rank)
+        ms4, g4, _, gm4 = sharded_pass(B, "comprehensive", v4, S4, 1024, ksteps, kwarm, placement=args.placement)
+        configs["config4"] = entry("comprehensive", "ComprehensiveFCParameters on 1 000 000 series x len 1024 in total, "
+                                   "%d series per rank (BASELINE.json configs[3], strong scaling)" % S4, S4, 1024, ms4, g4, "strong",
+                                   {"value": world * S4 / (ms4 / 1e3), "unit": "series/s", "placement": gm4.placement()})
+        del v4, gm4
+        torch.cuda.empty_cache()
+
+        # config 5: roll_time_series(rolling_direction=32, max_timeshift=255, min_timeshift=255) over 10 000 x 4096
+        # -> 1.21 M windows of 256 rows as (begin, len) views on the parents' buffer, sharded by parent
+        from tsfresh_b200 import _lib as lib5
+        from tsfresh_b200.distributed import shard_windows
+        P5, L5 = 10_000, 4096
+        t0 = time.perf_counter()
+        begin5 = (np.arange(P5, dtype=np.int64) * L5)
+        wb, wl, wp, we = lib5.roll_windows(begin5, np.full(P5, L5, dtype=np.int32), 32, 255, 255)
+        roll_ms = (time.perf_counter() - t0) * 1e3
+        lo5, hi5 = shard_windows(wp, P5, world, rank)
+        per5 = (len(wb) + world - 1) // world
+        n5 = hi5 - lo5
+        v5 = B.randn((P5, L5), 42 + 4)                       # every rank holds the (164 MB) parent buffer
+        wb_d = torch.from_numpy(wb[lo5:hi5].copy()).to(B.dev)
+        wl_d = torch.from_numpy(wl[lo5:hi5].copy()).to(B.dev)
+        ms5, g5, _, gm5 = sharded_pass(B, "comprehensive", v5.reshape(-1), n5, 256, ksteps, kwarm, csr=(wb_d, wl_d),
+                                       placement=args.placement)
+        nt = torch.tensor([n5], device=B.dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(nt)
+        configs["config5"] = entry("comprehensive", "roll_time_series(rolling_direction=32, max_timeshift=255, min_timeshift=255) over "
+                                   "10 000 series x len 4096 -> %d window views x 256 -> ComprehensiveFCParameters "
+                                   "(BASELINE.json configs[4]); windows sharded by parent" % len(wb), n5, 256, ms5, g5, "strong",
+                                   {"value": int(nt.item()) / (ms5 / 1e3), "unit": "windows/s", "windows": int(len(wb)),
+                                    "roll_windows_host_ms": roll_ms, "placement": gm5.placement()})
+        del v5, gm5, wb_d, wl_d
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        group_ms = {}
     if rank == 0:
-        peaks, which = measured_peaks()
         roofline = None
         groups = {}
+        tj = None
+        for tf in ("traffic_r2.json", "traffic_r1.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                tj["_file"] = tf
+                break
+            except Exception:
+                tj = None
+        same_workload = bool(tj) and (tj["workload"]["series"], tj["workload"]["len"], tj["workload"]["settings"]) == (S, L, args.settings)
         if group_ms:
             # algorithmic bytes per series of one kernel group: the 4*L value bytes it reads plus the 8 bytes per
             # output column it writes (DESIGN.md "Roofline"); whole pass: 4L + 12 + 8F
-            ncols = {}
-            from tsfresh_b200 import plan as planmod
-            for g, cnt in group_columns(plan).items():
-                ncols[g] = cnt
+            ncols = dict(group_columns(plan))
+            clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
             for g, ms in group_ms.items():
                 by = S * 16 * F if g == "assemble" else S * (4 * L + 8 * ncols.get(g, 0))
                 groups[g] = {"ms": ms, "columns": ncols.get(g, 0), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
+                ginst = tj.get("k_" + g, {}).get("inst_executed") if same_workload else None
+                if ginst:
+                    groups[g]["issue_frac"] = ginst / (ms * 1e-3) / (148 * 4 * clk)
             dom = max(group_ms, key=lambda g: group_ms[g])
             ach = groups[dom]["algorithmic_GBps"]
-            traffic, limiter = None, None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-                w = tj["workload"]
-                if (w["series"], w["len"], w["settings"]) == (S, L, args.settings) and ("k_" + dom) in tj:
-                    traffic = tj["k_" + dom]["traffic_bytes"] / 1e9
-                    limiter = "ncu: fp64 pipe %.0f%% active, issue %.0f%% active" % (
-                        tj["k_" + dom]["fp64_pipe_active_pct"], tj["k_" + dom]["issue_active_pct"])
-            except Exception:
-                pass
-            # supplementary compute roofline: these kernels are bound by instruction issue, not by HBM.  Warp
-            # instructions per launch come from the committed ncu capture of the same workload
-            # (smsp__inst_executed.sum, profiles/traffic_r1.json); the rate is measured live; the peak is
-            # 148 SMs x 4 schedulers x 1 warp instruction per clock at the sampled SM clock.
-            issue = None
-            try:
-                inst = tj["k_" + dom].get("inst_executed") if traffic is not None else None
-            except Exception:
-                inst = None
-            if inst:
-                clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-                peak_i = 148 * 4 * clk
-                a_i = inst / (group_ms[dom] * 1e-3)
-                issue = {"bound": "instruction issue", "achieved": a_i / 1e12, "peak": peak_i / 1e12,
-                         "unit": "T warp-inst/s", "frac": a_i / peak_i, "warp_inst_per_series": inst / S}
-            try:                                           # every group's issue-slot utilisation, same recipe
-                if (tj["workload"]["series"], tj["workload"]["len"], tj["workload"]["settings"]) == (S, L, args.settings):
-                    clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-                    for g in groups:
-                        ginst = tj.get("k_" + g, {}).get("inst_executed")
-                        if ginst:
-                            groups[g]["issue_frac"] = ginst / (groups[g]["ms"] * 1e-3) / (148 * 4 * clk)
-            except Exception:
-                pass
+            traffic, limiter, issue = None, None, None
+            if same_workload and ("k_" + dom) in tj:
+                kd = tj["k_" + dom]
+                traffic = kd["traffic_bytes"] / 1e9
+                limiter = "ncu (%s): fp64 pipe %.0f%% active, issue %.0f%% active" % (tj["_file"], kd["fp64_pipe_active_pct"], kd["issue_active_pct"])
+                if kd.get("inst_executed"):
+                    # supplementary compute roofline: warp instructions per launch from the committed ncu capture of the
+                    # same workload; rate measured live; peak = 148 SMs x 4 schedulers x 1 warp instruction per clock
+                    a_i = kd["inst_executed"] / (group_ms[dom] * 1e-3)
+                    issue = {"bound": "instruction issue", "achieved": a_i / 1e12, "peak": 148 * 4 * clk / 1e12,
+                             "unit": "T warp-inst/s", "frac": a_i / (148 * 4 * clk), "warp_inst_per_series": kd["inst_executed"] / S}
             roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                         "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650 GB/s",
                         "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
@@ -398,6 +537,20 @@ def main():
             if impute_info:
                 impute_info["frac_of_hbm_peak"] = impute_info["GBps"] / peaks["hbm_gbs"]
                 roofline["impute"] = impute_info
+            if "minimal" in configs:
+                # the reduction-only (class M) kernel: the kernel the north star's ">= 60 % of the HBM-read roofline" is about
+                gm_ = configs["minimal"]["groups_ms"]
+                plm, _ = B.plan("minimal")
+                kname = "moments" if "moments" in gm_ else "basic"
+                if kname in gm_:
+                    cols_m = group_columns(plm).get("basic", 0)
+                    bym = S * (4 * L + 8 * cols_m)
+                    roofline["minimal"] = {"kernel": "k_" + kname, "bound": "hbm", "ms": gm_[kname],
+                                           "achieved": bym / (gm_[kname] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                           "frac": bym / (gm_[kname] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "read_only_frac": S * 4 * L / (gm_[kname] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "algorithmic_GB_per_launch": bym / 1e9, "columns": cols_m,
+                                           "note": "class-M reductions of MinimalFCParameters at 1 M x 256; the median column is a sort (k_sorted), listed in configs.minimal.groups_ms"}
         cb = None
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(L, args.settings, args.cpu_seconds)
@@ -407,23 +560,25 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "columns": F, "global_series": world * S,
                        "l2": "inputs (%.2f GB) + outputs (%.2f GB) per step exceed the 126 MB L2" % (S * L * 4 / 1e9, S * F * 8 / 1e9),
-                       "parallelism": "ids sharded contiguously over %d rank(s)%s" % (world, "" if world == 1 else "; all-gather of the feature matrix per row block, overlapped")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline, "cpu_baseline": cb,
+                       "parallelism": "ids sharded contiguously over %d rank(s)%s" % (world, "" if world == 1 else
+                                      "; every rank's rows placed on every rank per row block by %s (tsfresh_b200.distributed.GatheredMatrix)" % placement)},
+            "clocks": clocks, "e2e": e2e, "e2e_long": e2e_long, "e2e_api": e2e_api,
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "cpu_baseline": cb, "configs": configs,
         }
-        if saved_stdout is not None:
+        if B.saved_stdout is not None:
             sys.stdout.flush()
             try:
                 import ctypes
                 ctypes.CDLL(None).fflush(None)       # whatever C code buffered for "stdout" leaves through stderr too
             except Exception:
                 pass
-            os.dup2(saved_stdout, 1)
+            os.dup2(B.saved_stdout, 1)
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
-        if saved_stdout is not None and rank != 0:
-            os.dup2(saved_stdout, 1)
+        if B.saved_stdout is not None and rank != 0:
+            os.dup2(B.saved_stdout, 1)
         dist.destroy_process_group()
 
 

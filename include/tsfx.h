@@ -183,6 +183,12 @@ int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, 
                      const int64_t* begin, const int32_t* len, int64_t n_series, double* out,
                      uint32_t flags);
 
+/* Device-pointer CSR calls size their working sets by the longest series.  Without a hint the library reduces `len` on
+ * the device and synchronises the stream once per call; a caller that knows an upper bound (e.g. max_timeshift + 1 for
+ * rolled windows) passes it here and the calls stay asynchronous.  The bound must hold for every series of the
+ * following device-pointer tsfx_extract_csr calls; 0 removes the hint. */
+int tsfx_set_max_len_hint(tsfx_ctx* ctx, int32_t max_len);
+
 /* Dense fast path: n_series series of identical length `len`, back to back. */
 int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_series,
                        int32_t len, double* out, uint32_t flags);

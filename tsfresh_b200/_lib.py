@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint"]
 
 
 def load():
@@ -69,6 +69,7 @@ def load():
         lib.tsfx_host_free.restype = None
         lib.tsfx_set_peer_outputs.argtypes = [vp, vp, i32, i32, ctypes.c_uint64, i32]
         lib.tsfx_peer_flush.argtypes = [vp]
+        lib.tsfx_set_max_len_hint.argtypes = [vp, i32]
         _lib = lib
         return lib
 
@@ -251,8 +252,10 @@ class DevicePlan:
                                              ctypes.c_void_p(out_ptr), flags)
         self.ctx.check(rc, "tsfx_extract_dense")
 
-    def extract_csr_device(self, values_ptr, n_values, begin_ptr, len_ptr, n_series, out_ptr, timing=False):
+    def extract_csr_device(self, values_ptr, n_values, begin_ptr, len_ptr, n_series, out_ptr, timing=False, max_len=0):
+        """max_len: upper bound of the series lengths if the caller knows one (keeps the call asynchronous)"""
         flags = FLAG_DEVICE_PTRS | (FLAG_TIMING if timing else 0)
+        self.ctx.check(self.ctx.lib.tsfx_set_max_len_hint(self.ctx.h, int(max_len)), "tsfx_set_max_len_hint")
         rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, ctypes.c_void_p(values_ptr), n_values,
                                            ctypes.c_void_p(begin_ptr), ctypes.c_void_p(len_ptr), n_series,
                                            ctypes.c_void_p(out_ptr), flags)

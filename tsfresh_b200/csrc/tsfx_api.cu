@@ -237,6 +237,7 @@ struct tsfx_ctx {
     ImputeWorkspace imp;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     int held_max_len = 0;
+    int max_len_hint = 0;        // tsfx_set_max_len_hint: longest series of the coming device-pointer CSR calls
     HostPool pool;
     Stager stager;
     // multi-GPU result placement (tsfx_set_peer_outputs): peers' mapped result matrices
@@ -740,8 +741,11 @@ extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const floa
     int max_len = 0;
     if (flags & TSFX_FLAG_DEVICE_PTRS) {
         R.values = values; R.begin = begin; R.len = len;
-        int rc2 = csr_max_len(ctx->csr, len, n_series, ctx->stream, &max_len);
-        if (rc2) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
+        if (ctx->max_len_hint > 0) max_len = ctx->max_len_hint;       // stays asynchronous
+        else {
+            int rc2 = csr_max_len(ctx->csr, len, n_series, ctx->stream, &max_len);
+            if (rc2) return fail(ctx, TSFX_E_CUDA, "max-length reduction failed");
+        }
         rc = run_groups(ctx, plan, R, max_len, out, flags);
         if (!rc && (flags & TSFX_FLAG_IMPUTE)) rc = impute_after_extract(ctx, out, n_series, plan->ncols);
         return rc;
@@ -1195,6 +1199,12 @@ extern "C" int tsfx_set_peer_outputs(tsfx_ctx* ctx, const uint64_t* peer_out, in
     ctx->peer_self = self_index;
     ctx->peer_mc = multicast_out;
     ctx->peer_mode = mode;
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_set_max_len_hint(tsfx_ctx* ctx, int32_t max_len) {
+    if (!ctx || max_len < 0) return TSFX_E_INVALID;
+    ctx->max_len_hint = max_len;
     return TSFX_OK;
 }
 

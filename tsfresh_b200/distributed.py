@@ -2,9 +2,15 @@
 
 The reference's own parallelism is data-parallel over lists of series (utilities/distribution.py:118-148,
 471-486); the series never interact, so the only exchange step is assembling the final
-[n_ids x n_features] matrix.  Rank r owns the contiguous row range shard_bounds(n, world, r); every rank
-extracts its rows with its own tsfx context and ONE all-gather of the (padded) row blocks rebuilds the full
-matrix on every rank (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).
+[n_ids x n_features] matrix.  Rank r owns the contiguous row range shard_bounds(n, world, r) and extracts its rows
+with its own tsfx context.
+
+Placement of the result (`GatheredMatrix`): the full matrix lives in symmetric memory (every rank maps every other
+rank's copy, torch.distributed._symmetric_memory).  The library's assemble pass writes each finished row block into
+the local copy AND into the peers' copies (tsfx_set_peer_outputs: one multicast store through the NVSwitch, or copy
+engines / P2P stores over NVLink), block by block while the kernels of the next block run -- there is no separate
+collective kernel and no second pass over the matrix.  Without symmetric memory (CPU tests with gloo, or a box
+without P2P) the same row blocks are exchanged with all_gather_into_tensor on a side stream.
 """
 import torch
 import torch.distributed as dist
@@ -50,9 +56,26 @@ def extract_dense_sharded(values, fc_parameters, device=None, group=None):
     plan = Plan(fc_parameters)
     ctx = get_context(device)
     dp = _device_plan(ctx, plan)
+    dev = torch.device("cuda", ctx.device)
+    per = shard_rows(n, world)
+    if dist.get_backend(group) == "nccl" and hi > lo:
+        # device path: this rank's rows are placed on every rank while the later row blocks are still being computed
+        gm = GatheredMatrix(per, plan.n_cols, dev, group)
+        local = torch.from_numpy(np.ascontiguousarray(values[lo:hi], dtype=np.float32)).to(dev)
+        if hi - lo < per:
+            gm.local[hi - lo:].fill_(float("nan"))
+        torch.cuda.synchronize(dev)                 # the library launches on its own stream
+        gm.attach(ctx)
+        try:
+            extract_dense_sharded_device(dp, local, gm)
+            gm.finish(ctx)
+        finally:
+            gm.detach(ctx)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+        return plan.suffixes, gm.full[:n]
     local = dp.extract_dense(np.ascontiguousarray(values[lo:hi], dtype=np.float32)) if hi > lo else \
         np.empty((0, plan.n_cols))
-    dev = torch.device("cuda", ctx.device)
     full = gather_rows(torch.from_numpy(local).to(dev), n, group)
     return plan.suffixes, full
 
@@ -77,3 +100,135 @@ def shard_windows(parent, n_parents, world, rank):
     for r in range(1, len(cuts)):                                 # monotone (small inputs: several ranks may be empty)
         cuts[r] = max(cuts[r], cuts[r - 1])
     return cuts[rank], cuts[rank + 1]
+
+
+class GatheredMatrix:
+    """The [world * rows_per_rank, n_cols] float64 feature matrix, replicated on every rank's GPU.
+
+        gm = GatheredMatrix(rows_per_rank, n_cols, device)        # collective: every rank constructs it
+        gm.attach(ctx)                                            # rows written by ctx now also land on the peers
+        ... dp.extract_*_device(..., out_ptr=gm.local_ptr(row)) ...
+        gm.finish(ctx)                                            # all ranks' rows are in gm.full after this
+    """
+
+    def __init__(self, rows_per_rank, n_cols, device, group=None, mode="auto", n_blocks=8):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows, self.n_cols, self.device = int(rows_per_rank), int(n_cols), device
+        self.kind, self.hdl, self.peer_ptrs, self.mc_ptr = "local", None, None, 0
+        self.mode = mode
+        self.n_blocks = n_blocks
+        self._pending = []                 # (lo, hi) row blocks not yet exchanged (nccl fallback)
+        self._comm = None
+        shape = (self.world * self.rows, self.n_cols)
+        if self.world > 1 and device.type == "cuda" and mode != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self.full = symm.empty(shape, dtype=torch.float64, device=device)
+                self.hdl = symm.rendezvous(self.full, group if group is not None else dist.group.WORLD)
+                self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                try:
+                    self.mc_ptr = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support(device.type, device.index) else 0
+                except Exception:
+                    self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+                self.kind = "peer"
+            except Exception as e:            # no symmetric memory on this box: NCCL exchange of the row blocks
+                self.why_not_peer = repr(e)
+                self.full = torch.empty(shape, dtype=torch.float64, device=device)
+                self.kind = "nccl"
+        else:
+            self.full = torch.empty(shape, dtype=torch.float64, device=device)
+            self.kind = "nccl" if self.world > 1 else "local"
+        if self.kind == "nccl" and device.type == "cuda":
+            self._comm = torch.cuda.Stream(device=device)
+
+    @property
+    def local(self):
+        return self.full[self.rank * self.rows:(self.rank + 1) * self.rows]
+
+    def local_ptr(self, row=0):
+        return self.local.data_ptr() + int(row) * self.n_cols * 8
+
+    def placement(self):
+        from . import _lib
+        if self.kind != "peer":
+            return self.kind
+        want = {"auto": _lib.PEER_AUTO, "copy": _lib.PEER_COPY, "store": _lib.PEER_STORE, "multicast": _lib.PEER_MULTICAST}[self.mode]
+        if want == _lib.PEER_AUTO:
+            want = _lib.PEER_MULTICAST if self.mc_ptr else _lib.PEER_COPY
+        return {_lib.PEER_COPY: "copy engines over NVLink", _lib.PEER_STORE: "P2P stores from the assemble kernel",
+                _lib.PEER_MULTICAST: "multicast stores from the assemble kernel (NVSwitch)"}[want]
+
+    def attach(self, ctx):
+        from . import _lib
+        if self.kind == "peer":
+            mode = {"auto": _lib.PEER_AUTO, "copy": _lib.PEER_COPY, "store": _lib.PEER_STORE,
+                    "multicast": _lib.PEER_MULTICAST}[self.mode]
+            ctx.set_peer_outputs(self.peer_ptrs, self.rank, self.mc_ptr, mode)
+
+    def detach(self, ctx):
+        if self.kind == "peer":
+            ctx.set_peer_outputs([], 0)
+
+    def block_done(self, lo, hi, stream):
+        """rows [lo, hi) of the local shard are final on `stream` (nccl fallback: exchange them now, overlapped)"""
+        if self.kind != "nccl":
+            return
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            stage = torch.empty((self.world, hi - lo, self.n_cols), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(stage.view(-1), self.local[lo:hi].reshape(-1), group=self.group)
+            self.full.view(self.world, self.rows, self.n_cols)[:, lo:hi].copy_(stage)
+
+    def finish(self, ctx, stream=None, ctx_on_current_stream=False):
+        """Every rank's rows are visible in self.full on every rank once this returns (and the stream has run).
+        ctx_on_current_stream: the context was created on torch's current stream, so the barrier below is ordered
+        after the placement by stream order; otherwise the context's stream is synchronised first."""
+        if self.kind == "peer":
+            ctx.peer_flush()
+            if not ctx_on_current_stream:
+                ctx.sync()
+            self.hdl.barrier(channel=0)
+        elif self.kind == "nccl" and self._comm is not None:
+            (stream or torch.cuda.current_stream(self.device)).wait_stream(self._comm)
+
+
+def extract_dense_sharded_device(dp, values, gm, stream=None, ctx_on_current_stream=False):
+    """values: this rank's [rows, L] float32 CUDA tensor; dp: DevicePlan on a context created on `stream`.
+    Runs the pass in gm.n_blocks row blocks (so that placement / exchange of block b overlaps the kernels of block
+    b + 1) and leaves this rank's rows everywhere (gm)."""
+    S, L = values.shape
+    stream = stream or torch.cuda.current_stream(values.device)
+    nb = gm.n_blocks if gm.world > 1 else 1
+    bs = (S + nb - 1) // nb
+    for b in range(nb):
+        lo, hi = b * bs, min(S, (b + 1) * bs)
+        if lo >= hi:
+            break
+        dp.extract_dense_device(values[lo:hi].data_ptr(), hi - lo, L, gm.local_ptr(lo))
+        if gm.kind == "nccl" and not ctx_on_current_stream:
+            dp.ctx.sync()                  # the library ran on its own stream: order the exchange after it
+        gm.block_done(lo, hi, stream)
+    return nb
+
+
+def extract_csr_sharded_device(dp, values, begin, length, gm, stream=None, ctx_on_current_stream=False, max_len=0):
+    """Same for a CSR shard (e.g. rolled windows sharded by parent, shard_windows): begin / length are this rank's
+    int64 / int32 CUDA tensors over the shared `values` buffer."""
+    S = int(begin.shape[0])
+    stream = stream or torch.cuda.current_stream(values.device)
+    nb = gm.n_blocks if gm.world > 1 else 1
+    bs = (S + nb - 1) // nb
+    for b in range(nb):
+        lo, hi = b * bs, min(S, (b + 1) * bs)
+        if lo >= hi:
+            break
+        dp.extract_csr_device(values.data_ptr(), values.numel(), begin[lo:hi].data_ptr(), length[lo:hi].data_ptr(), hi - lo,
+                              gm.local_ptr(lo), max_len=max_len)
+        if gm.kind == "nccl" and not ctx_on_current_stream:
+            dp.ctx.sync()                  # the library ran on its own stream: order the exchange after it
+        gm.block_done(lo, hi, stream)
+    return nb
