@@ -137,6 +137,8 @@ enum tsfx_calc {
     TSFX_COUNT_BELOW,                                  /* :2325 p0=t */
     TSFX_BENFORD_CORRELATION,                          /* :2341 */
     TSFX_QUERY_SIMILARITY_COUNT,                       /* :2475 default query=None -> NaN */
+    TSFX_LINEAR_TREND_TIMEWISE,                        /* :2274 attr=linregress attr; regressor = row time in hours
+                                                        * since the first row of the series (tsfx_set_row_times) */
     TSFX_CONST_NAN,                                    /* a column the reference defines as NaN */
     TSFX_N_CALCS
 };
@@ -188,6 +190,13 @@ int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, 
  * rolled windows) passes it here and the calls stay asynchronous.  The bound must hold for every series of the
  * following device-pointer tsfx_extract_csr calls; 0 removes the hint. */
 int tsfx_set_max_len_hint(tsfx_ctx* ctx, int32_t max_len);
+
+/* Row timestamps for linear_trend_timewise (feature_calculators.py:2274-2306: the regressor is the series' DatetimeIndex,
+ * hours since its first row).  row_time_ns[i] is the timestamp (int64 nanoseconds) of row i of the `values` array of the
+ * NEXT extract call on this context (host pointer, or device pointer with TSFX_FLAG_DEVICE_PTRS); that call consumes
+ * them (tsfx_extract_long carries them through its sort).  A plan with linear_trend_timewise columns and no row times
+ * is TSFX_E_INVALID. */
+int tsfx_set_row_times(tsfx_ctx* ctx, const int64_t* row_time_ns, int64_t n_rows, uint32_t flags);
 
 /* Dense fast path: n_series series of identical length `len`, back to back. */
 int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const float* values, int64_t n_series,

@@ -519,6 +519,13 @@ def linear_trend(x, param):  # :1343-1366
     return [getattr(lr, p["attr"]) for p in param]
 
 
+def linear_trend_timewise(x, times_ns, param):  # :2274-2306; times_ns: the series' DatetimeIndex as int64 nanoseconds
+    ix = pd.DatetimeIndex(np.asarray(times_ns, dtype="datetime64[ns]"))
+    times_hours = np.asarray((ix - ix[0]).total_seconds() / float(3600))
+    lr = linregress(times_hours, np.asarray(x, dtype=np.float64))
+    return [getattr(lr, p["attr"]) for p in param]
+
+
 @combiner
 def agg_linear_trend(x, param):  # :2171-2222 with _aggregate_on_chunks :176-193
     cache, out = {}, []

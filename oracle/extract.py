@@ -25,16 +25,21 @@ def is_exact_column(suffix):
     return name in EXACT_CALCULATORS or suffix.startswith('augmented_dickey_fuller__attr_"usedlag"')
 
 
-def oracle_rows(series, fc_parameters, skip=("linear_trend_timewise",)):
-    """series: iterable of 1-D arrays.  Returns float64 matrix [n_series x n_columns]."""
+def oracle_rows(series, fc_parameters, skip=("linear_trend_timewise",), times=None):
+    """series: iterable of 1-D arrays.  Returns float64 matrix [n_series x n_columns].
+    times: per-series int64 nanosecond timestamps (the frame's DatetimeIndex); with them linear_trend_timewise is
+    evaluated (extraction.py:349-361 skips it, with a warning, when the index is not a DatetimeIndex)."""
     rows = []
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         with np.errstate(all="ignore"):
-            for x in series:
+            for k, x in enumerate(series):
                 x = np.asarray(x, dtype=np.float64)
                 row = []
                 for name, params in fc_parameters.items():
+                    if name == "linear_trend_timewise" and times is not None:
+                        row.extend(float(v) for v in calculators.linear_trend_timewise(x, times[k], params))
+                        continue
                     if name in skip:
                         continue
                     row.extend(calculators.evaluate(name, x, params))

@@ -212,3 +212,29 @@ def test_csr_tsdata_seam():
     assert list(X.columns) == ["value__maximum", "value__median"] and list(X.index) == [3, 5, 8, 13, 21]
     np.testing.assert_array_equal(X["value__maximum"].to_numpy(), [float(s.max()) for s in series])
     np.testing.assert_array_equal(X["value__median"].to_numpy(), [float(np.median(s.astype(np.float64))) for s in series])
+
+
+def test_linear_trend_timewise_on_a_datetime_index():
+    """feature_calculators.py:2274-2306 through extract_features: golden values of the unmodified reference
+    (tests/golden/timewise.npz, oracle/make_golden_timewise.py), rows in order and shuffled (the timestamps follow
+    the device sort), and the no-DatetimeIndex case (skipped with a warning, extraction.py:349-358)."""
+    import os
+    import warnings
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "timewise.npz"), allow_pickle=True)
+    fc = {"linear_trend_timewise": [{"attr": a} for a in ("pvalue", "rvalue", "intercept", "slope", "stderr")],
+          "mean": None, "linear_trend": [{"attr": "slope"}]}
+    df = pd.DataFrame({"id": z["id"], "value": z["value"]}, index=pd.DatetimeIndex(z["t_ns"].astype("datetime64[ns]")))
+    for frame in (df, df.sample(frac=1.0, random_state=3)):
+        # without a sort column the reference keeps the row order inside each id: shuffle whole frames only by id blocks
+        if frame is not df:
+            frame = pd.concat([g for _, g in sorted(df.groupby("id"), key=lambda kv: -kv[0])])
+        X = extract_features(frame, column_id="id", default_fc_parameters=fc)
+        assert list(X.columns) == list(z["columns"]) and list(X.index) == list(z["index"])
+        suffixes = [c.split("__", 1)[1] for c in X.columns]
+        bad = compare(X.to_numpy(), z["reference"], suffixes)
+        assert not bad, bad[:20]
+    plain = df.reset_index(drop=True)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        X = extract_features(plain, column_id="id", default_fc_parameters=fc, show_warnings=True)
+    assert [c for c in X.columns if "timewise" in c] == [] and any("DatetimeIndex" in str(m.message) for m in w)

@@ -83,8 +83,9 @@ def test_nan_values_are_an_error(env):
     perm = rng.permutation(len(ids))
     with pytest.raises(ValueError, match="contains NaN"):
         dp.extract_long(ids[perm], t[perm], v[perm])
+    mid = (len(v) // 2 // 10) * 10
     with pytest.raises(ValueError, match="contains NaN"):
-        dp.extract_dense(v[:4000].reshape(400, 10))
+        dp.extract_dense(v[mid - 2000:mid + 2000].reshape(400, 10))
     uid, start, cnt = np.unique(ids, return_index=True, return_counts=True)
     with pytest.raises(ValueError, match="contains NaN"):
         dp.extract_csr(v, start.astype(np.int64), cnt.astype(np.int32))

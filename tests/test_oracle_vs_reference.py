@@ -184,3 +184,25 @@ def test_from_columns_matches_reference():
             from_columns(bad)
         with pytest.raises(err):
             rs.from_columns(bad)
+
+
+def test_linear_trend_timewise_matches_reference():
+    """feature_calculators.py:2274-2306 with its own known answers (test_feature_calculations.py:1796-1935) and on
+    irregularly sampled random series"""
+    import pandas as pd
+    from oracle import calculators as C
+    ref = ref_shim.load()
+    from tsfresh.feature_extraction.feature_calculators import linear_trend_timewise
+    param = [{"attr": a} for a in ("pvalue", "rvalue", "intercept", "slope", "stderr")]
+    x = pd.Series([0, 1, 3, 6], index=pd.DatetimeIndex(["2018-01-01 04:00:00", "2018-01-01 05:00:00", "2018-01-01 07:00:00",
+                                                         "2018-01-01 10:00:00"]))
+    got = C.linear_trend_timewise(x.to_numpy(), x.index.as_unit("ns").asi8, param)
+    assert got[3] == pytest.approx(1.0, abs=1e-3) and got[2] == pytest.approx(0.0, abs=1e-3)
+    rng = np.random.default_rng(12)
+    for n in (2, 3, 17, 256):
+        gaps = rng.integers(1, 5000, n).cumsum() * 10 ** 9 + rng.integers(0, 10 ** 9, n)
+        ix = pd.DatetimeIndex(np.sort(gaps).astype("datetime64[ns]"))
+        s = pd.Series(rng.standard_normal(n).astype(np.float32).astype(np.float64), index=ix)
+        want = [v for _, v in linear_trend_timewise(s, param)]
+        got = C.linear_trend_timewise(s.to_numpy(), ix.asi8, param)
+        np.testing.assert_allclose(got, want, rtol=1e-12, equal_nan=True)

@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times"]
 
 
 def load():
@@ -70,6 +70,7 @@ def load():
         lib.tsfx_set_peer_outputs.argtypes = [vp, vp, i32, i32, ctypes.c_uint64, i32]
         lib.tsfx_peer_flush.argtypes = [vp]
         lib.tsfx_set_max_len_hint.argtypes = [vp, i32]
+        lib.tsfx_set_row_times.argtypes = [vp, vp, i64, u32]
         _lib = lib
         return lib
 
@@ -168,6 +169,11 @@ class Context:
         weakref.finalize(buf, lambda lib=lib, h=h, p=p: lib.tsfx_host_free(h, ctypes.c_void_p(p)))
         return arr
 
+    def set_row_times(self, times_ns):
+        """timestamps (int64 ns) of the rows of the NEXT extract call's values (linear_trend_timewise)"""
+        t = np.ascontiguousarray(times_ns, dtype=np.int64)
+        self.check(self.lib.tsfx_set_row_times(self.h, _ptr(t), len(t), 0), "tsfx_set_row_times")
+
     # ---- multi-GPU result placement (tsfx_set_peer_outputs)
     def set_peer_outputs(self, peer_ptrs, self_index, multicast_ptr=0, mode=PEER_AUTO):
         arr = (ctypes.c_uint64 * max(1, len(peer_ptrs)))(*[int(x) for x in peer_ptrs])
@@ -199,12 +205,14 @@ class DevicePlan:
             self.h = None
 
     # ---- host-pointer entry points -------------------------------------------------------------
-    def extract_csr(self, values, begin, length, flags=0):
+    def extract_csr(self, values, begin, length, flags=0, times=None):
         values = np.ascontiguousarray(values, dtype=np.float32)
         begin = np.ascontiguousarray(begin, dtype=np.int64)
         length = np.ascontiguousarray(length, dtype=np.int32)
         out = np.empty((len(begin), self.n_cols), dtype=np.float64)
         with self.ctx.lock:
+            if times is not None:
+                self.ctx.set_row_times(times)
             rc = self.ctx.lib.tsfx_extract_csr(self.ctx.h, self.h, _ptr(values), values.size, _ptr(begin), _ptr(length),
                                                len(begin), _ptr(out), flags)
             self.ctx.check(rc, "tsfx_extract_csr")
@@ -220,9 +228,10 @@ class DevicePlan:
             self.ctx.check(rc, "tsfx_extract_dense")
         return out
 
-    def extract_long(self, ids, sort_keys, values, flags=0):
+    def extract_long(self, ids, sort_keys, values, flags=0, times=None):
         """(id, sort key, value) rows in any order -> (unique ids ascending, [n_ids x n_cols] matrix).  One C call
-        (tsfx_extract_long_alloc): the library sizes the result and returns it on pinned host memory."""
+        (tsfx_extract_long_alloc): the library sizes the result and returns it on pinned host memory.
+        times: int64 ns timestamp of every row (the frame's DatetimeIndex) when the plan has linear_trend_timewise."""
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         values = np.ascontiguousarray(values, dtype=np.float32)
         is_f64 = 0
@@ -237,6 +246,8 @@ class DevicePlan:
         p_ids, p_out = ctypes.c_void_p(), ctypes.c_void_p()
         ctx = self.ctx
         with ctx.lock:
+            if times is not None:
+                ctx.set_row_times(times)
             rc = ctx.lib.tsfx_extract_long_alloc(ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids),
                                                  ctypes.byref(p_ids), ctypes.byref(p_out), ctypes.byref(n_series), flags)
             ctx.check(rc, "tsfx_extract_long")

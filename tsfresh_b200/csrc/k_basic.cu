@@ -715,6 +715,38 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                         for (int t = lane; t < run; t += 32) orow[j + t] = m_linreg_pick(fit, A.descs[j + t].attr);
                     break;
                 }
+                case TSFX_LINEAR_TREND_TIMEWISE: {
+                    // linregress(hours since the first row, x) (:2296-2301): the regressor is
+                    // (ix - ix[0]).total_seconds() / 3600 = ns / 1e9 / 3600, two correctly rounded divisions as pandas does
+                    used = run;
+                    stored = true;
+                    LinReg fit;
+                    bool have = A.R.times != nullptr;
+                    if (have) {
+                        const int64_t b0 = A.R.begin ? A.R.begin[s] : s * (int64_t)A.R.dense_len;
+                        const int64_t* tp = A.R.times + b0;
+                        const int64_t t0 = tp[0];
+                        double st = 0.0;
+                        for (int i = lane; i < n; i += 32) {
+                            const double th = __ddiv_rn(__ddiv_rn((double)(tp[i] - t0), 1e9), 3600.0);
+                            scr[i] = th;
+                            st += th;
+                        }
+                        const double tm = wsum(st) / dn;
+                        double sxx = 0.0, sxy = 0.0;
+                        for (int i = lane; i < n; i += 32) {
+                            const double dt = scr[i] - tm;
+                            sxx = fma(dt, dt, sxx);
+                            sxy = fma(dt, xc[i], sxy);
+                        }
+                        sxx = wsum(sxx) / dn;
+                        sxy = wsum(sxy) / dn;
+                        fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
+                    }
+                    if (live)
+                        for (int t = lane; t < run; t += 32) orow[j + t] = have ? m_linreg_pick(fit, A.descs[j + t].attr) : dnan();
+                    break;
+                }
                 case TSFX_AGG_LINEAR_TREND: {
                     // stage A, warp-uniform: the regression sums of every distinct (f_agg, chunk_len) of the run -> altS;
                     // stage B, one descriptor per lane: linregress of its key's sums and the attribute it asks for

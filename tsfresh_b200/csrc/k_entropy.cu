@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 3 : 1)) k_entropy(Entrop
 template <int G>
 __device__ __forceinline__ void gsync() { if (G == 1) __syncwarp(); else __syncthreads(); }
 
-__device__ __forceinline__ unsigned f32_key(float f) {
-    const unsigned u = __float_as_uint(f);
+__device__ __forceinline__ unsigned f32_key(float f) {      // order-preserving; -0.0 and +0.0 share one key
+    unsigned u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float key_f32(unsigned k) {
@@ -227,7 +228,7 @@ __device__ __forceinline__ float key_f32(unsigned k) {
 }
 
 struct RankLayout {            // byte offsets inside one series' working region
-    int t_off, s_off, pi_off, rk_off, lh_off, red_off, bytes;
+    int t_off, s_off, pi_off, rk_off, lh_off, cnt_off, red_off, bytes;
     int rs;                    // row stride of T in 32-bit words (multiple of 4, odd multiple of 16 bytes)
 };
 __host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
@@ -242,10 +243,11 @@ __host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
     if (tb < n2 * 8) tb = n2 * 8;                  // the sort keys alias the table
     int o = 0;
     L.t_off = o; o += (tb + 15) & ~15;
-    L.s_off = o; o += ((nmax + 1) * 8 + 15) & ~15;
+    L.s_off = o; o += (n2 * 4 + 15) & ~15;                     // sorted keys (uint32), 0xffffffff beyond n
     L.pi_off = o; o += (n2 * 2 + 15) & ~15;
     L.rk_off = o; o += ((nmax + 2) * 2 + 15) & ~15;
     L.lh_off = o; o += (((nmax + 3) & ~3) * 4 + 15) & ~15;   // lo | (hi+1) << 16 per rank; aliases the float32 staging copy
+    L.cnt_off = o; o += ((nmax + 2) * 4 + 15) & ~15;           // histogram of the interval starts
     L.red_off = o; o += (G > 1) ? G * 4 * 8 : 0;
     L.bytes = (o + 15) & ~15;
     return L;
@@ -264,10 +266,11 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1)))
     unsigned char* base = smem_raw + (((A.npad + 1) * 8 + 15) & ~15) + (size_t)grp * L.bytes;
     unsigned* T = reinterpret_cast<unsigned*>(base + L.t_off);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + L.t_off);
-    double* s64 = reinterpret_cast<double*>(base + L.s_off);
+    unsigned* sk = reinterpret_cast<unsigned*>(base + L.s_off);
     unsigned short* pi = reinterpret_cast<unsigned short*>(base + L.pi_off);
     unsigned short* rk = reinterpret_cast<unsigned short*>(base + L.rk_off);
     unsigned* lohi = reinterpret_cast<unsigned*>(base + L.lh_off);
+    unsigned* cnt = reinterpret_cast<unsigned*>(base + L.cnt_off);
     float* xs = reinterpret_cast<float*>(base + L.lh_off);
     double* red = reinterpret_cast<double*>(base + L.red_off);
     const int RS = L.rs;
@@ -304,16 +307,18 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1)))
                 gsync<G>();
             }
         }
-        // sorted values (float64 for the searches), rank <-> time maps.  keys alias T: read everything before T is built
-        const int per = (n + NTHR - 1) / NTHR;
+        // sorted keys (for the searches), rank <-> time maps.  keys alias T: read everything before T is built
+        const int per = (N2 + NTHR - 1) / NTHR;
         for (int q = 0; q < per; ++q) {
             const int a = tid + q * NTHR;
-            unsigned long long kv = a < n ? keys[a] : 0ull;
-            if (a < n) {
-                const unsigned idx = (unsigned)kv;
-                s64[a] = (double)key_f32((unsigned)(kv >> 32));
-                pi[a] = (unsigned short)idx;
-                rk[idx] = (unsigned short)a;
+            if (a < N2) {
+                const unsigned long long kv = keys[a];
+                sk[a] = (unsigned)(kv >> 32);              // 0xffffffff beyond n
+                if (a < n) {
+                    const unsigned idx = (unsigned)kv;
+                    pi[a] = (unsigned short)idx;
+                    rk[idx] = (unsigned short)a;
+                }
             }
         }
         gsync<G>();
@@ -356,27 +361,72 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1)))
         gsync<G>();
         double* orow = A.out + (size_t)s * A.ncols;
         const int n2 = n - 1, n3 = n - 2;
-        int steps = 0;
-        while ((1 << steps) < n) ++steps;                    // search steps: 2^steps >= n
         for (int dj = 0; dj < A.nd; ++dj) {
             const Desc d = A.descs[dj];
             const double tau = (d.calc == TSFX_SAMPLE_ENTROPY) ? 0.2 * M.sd : d.p0 * M.sd;
             const bool sane = tau >= 0.0;                    // NaN / negative tolerance: every comparison is false
-            // ---- phase A: rank interval of every rank (two branch-free binary searches with numpy's predicate)
-            for (int r = tid; r < n; r += NTHR) {
-                unsigned v = 0x00010001u;                    // empty: T[1] & ~T[1]
-                if (sane) {
-                    const double sr = s64[r];
-                    int hi = r, lo = r;
-                    for (int st = steps - 1; st >= 0; --st) {
-                        const int c = hi + (1 << st);
-                        if (c < n && (s64[c] - sr) <= tau) hi = c;
-                        const int e = lo - (1 << st);
-                        if (e >= 0 && (sr - s64[e]) <= tau) lo = e;
+            // ---- phase A: rank interval [lo, hi] of every rank r.
+            // lo(r) = #{ a : x_(a) < L_r } where L_r is the smallest float32 y with fl64(x_(r) - y) <= tau (the predicate is
+            // monotone in y, so the interval is exact): L_r = round-up of x_(r) - tau, corrected by at most one float32
+            // step with the exact predicate, then ONE binary search over the sorted keys.  hi needs no second search:
+            // the relation is symmetric (a <= hi(r) <=> lo(a) <= r), so hi(r) + 1 = #{ a : lo(a) <= r } = the inclusive
+            // prefix sum of the histogram of lo.
+            for (int r = tid; r <= n; r += NTHR) cnt[r] = 0u;
+            gsync<G>();
+            if (sane) {
+                constexpr int U = 4;                                 // ranks per lane in flight (independent chains)
+                for (int r0 = tid; r0 < n; r0 += U * NTHR) {
+                    unsigned kL[U];
+                    int pos[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * NTHR;
+                        const double sr = (double)key_f32(sk[r < n ? r : 0]);
+                        float Lf = __double2float_ru(sr - tau);
+                        if (!((sr - (double)Lf) <= tau)) Lf = key_f32(f32_key(Lf) + 1u);       // one float32 step up
+                        else {
+                            const float Lp = key_f32(f32_key(Lf) - 1u);                          // one step down still inside?
+                            if ((sr - (double)Lp) <= tau) Lf = Lp;
+                        }
+                        kL[u] = f32_key(Lf);
+                        pos[u] = 0;
                     }
-                    v = (unsigned)lo | ((unsigned)(hi + 1) << 16);
+                    for (int st = N2 >> 1; st > 0; st >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (sk[pos[u] + st - 1] < kL[u]) pos[u] += st;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * NTHR;
+                        if (r < n) {
+                            // (N2 a power of two >= n: the search above covers [0, N2 - 1]; a count of N2 - 1 < n can only
+                            // be short by the last element, checked here)
+                            int lo = pos[u];
+                            if (lo == N2 - 1 && sk[N2 - 1] < kL[u]) lo = N2;
+                            lohi[r] = (unsigned)lo;
+                            atomicAdd(&cnt[lo], 1u);
+                        }
+                    }
                 }
-                lohi[r] = v;
+            }
+            gsync<G>();
+            if (gw == 0) {              // inclusive scan of the histogram by one warp: lane l owns a contiguous run of ranks
+                const int run = (n + 31) >> 5;
+                const int b0 = lane * run;
+                unsigned tot = 0u;
+                for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
+                unsigned inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+                unsigned acc = inc - tot;
+                for (int k = 0; k < run; ++k) {
+                    const int r = b0 + k;
+                    if (r < n) {
+                        acc += cnt[r];
+                        lohi[r] = sane ? (lohi[r] | (acc << 16)) : 0x00010001u;       // lo | (hi + 1) << 16; empty: T[1] & ~T[1]
+                    }
+                }
             }
             gsync<G>();
             // ---- phase B: template counts, lane = row (30 rows per block: rows i+1, i+2 come from the next lanes)

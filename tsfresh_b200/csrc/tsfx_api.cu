@@ -237,6 +237,10 @@ struct tsfx_ctx {
     ImputeWorkspace imp;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     int held_max_len = 0;
+    bool used_moments = false;   // the last pass ran k_moments in place of k_basic (reported as "moments")
+    DevBuf times, times_sorted;  // tsfx_set_row_times: row timestamps of the next extract call (linear_trend_timewise)
+    const int64_t* times_ptr = nullptr;
+    int64_t times_rows = -1;
     int max_len_hint = 0;        // tsfx_set_max_len_hint: longest series of the coming device-pointer CSR calls
     HostPool pool;
     Stager stager;
@@ -257,6 +261,9 @@ struct tsfx_plan {
     std::vector<Desc> host[G_COUNT];
     Desc* dev[G_COUNT] = {nullptr};
     int32_t* d_final_col = nullptr;   // final column of every staged column, groups concatenated
+    bool basic_moments_only = false;  // the BASIC group is reductions only: k_moments replaces k_basic
+    int moments_need_high = 0;
+    int n_groups_used = 0;
     int basic_nfin = 0;               // leading "finisher" descriptors of the BASIC group
     int sorted_nfin = 0;              // same for the SORTED group
     int spectral_nfft = 0;            // leading fft_coefficient descriptors of the SPECTRAL group
@@ -267,6 +274,7 @@ struct tsfx_plan {
     int need_fft = 0, need_welch = 0;
     int max_ar_k = 0, need_adf = 0;
     int max_lz_bins = 0, max_perm_dim = 0, max_cwt_peaks_n = 0, n_lz = 0;
+    int need_times = 0;               // linear_trend_timewise columns: the extract call needs tsfx_set_row_times
     int friedrich_r = 0;
     double* d_tables = nullptr;
     int64_t* d_toff = nullptr;
@@ -375,6 +383,7 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release(); ctx->stage.release();
+    ctx->times.release(); ctx->times_sorted.release();
     ctx->csr.release();
     ctx->imp.release();
     ctx->stager.release();
@@ -439,6 +448,7 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
                 P->max_ar_k = std::max(P->max_ar_k, d.i1);
                 break;
             case TSFX_AUGMENTED_DICKEY_FULLER: P->need_adf = 1; break;
+            case TSFX_LINEAR_TREND_TIMEWISE: P->need_times = 1; break;
             case TSFX_APPROXIMATE_ENTROPY:
                 if (d.i0 != 2) { delete P; return fail(ctx, TSFX_E_UNSUPPORTED, "approximate_entropy: only m=2"); }
                 break;
@@ -501,6 +511,13 @@ extern "C" int tsfx_plan_create(tsfx_ctx* ctx, const tsfx_feature_desc* descs, i
             if (e != cudaSuccess) { tsfx_plan_destroy(P); return fail(ctx, TSFX_E_CUDA, cudaGetErrorString(e)); }
         }
     }
+    P->basic_moments_only = !P->host[G_BASIC].empty();
+    for (const Desc& d : P->host[G_BASIC]) {
+        if (!moments_only_calc(d.calc)) P->basic_moments_only = false;
+        if (d.calc == TSFX_SKEWNESS || d.calc == TSFX_KURTOSIS) P->moments_need_high = 1;
+    }
+    { const char* e = getenv("TSFX_NO_MOMENTS_KERNEL"); if (e && e[0] == '1') P->basic_moments_only = false; }
+    for (int g = 0; g < G_COUNT; ++g) P->n_groups_used += P->host[g].empty() ? 0 : 1;
     if (!final_col.empty()) {
         cudaError_t e = cudaMalloc(&P->d_final_col, final_col.size() * sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMemcpy(P->d_final_col, final_col.data(), final_col.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -547,6 +564,35 @@ static int ensure_twiddle(tsfx_ctx* ctx, int n_pow2) {
     return TSFX_OK;
 }
 
+// row timestamps handed over with tsfx_set_row_times for a call whose `values` array has `rows` rows (consumed)
+static int take_times(tsfx_ctx* ctx, const tsfx_plan* P, int64_t rows, const int64_t** out) {
+    *out = nullptr;
+    const bool have = ctx->times_rows >= 0;
+    const int64_t got = ctx->times_rows;
+    const int64_t* p = ctx->times_ptr;
+    ctx->times_rows = -1;
+    ctx->times_ptr = nullptr;
+    if (!P->need_times) return TSFX_OK;
+    if (!have) return fail(ctx, TSFX_E_INVALID, "linear_trend_timewise needs the row timestamps (tsfx_set_row_times)");
+    if (got != rows) return fail(ctx, TSFX_E_INVALID, "tsfx_set_row_times: " + std::to_string(got) + " timestamps for " + std::to_string(rows) + " rows");
+    *out = p;
+    return TSFX_OK;
+}
+
+extern "C" int tsfx_set_row_times(tsfx_ctx* ctx, const int64_t* row_time_ns, int64_t n_rows, uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (n_rows < 0 || (n_rows > 0 && !row_time_ns)) return fail(ctx, TSFX_E_INVALID, "tsfx_set_row_times: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (flags & TSFX_FLAG_DEVICE_PTRS) ctx->times_ptr = row_time_ns;
+    else {
+        CK(ctx->times.reserve(std::max<size_t>((size_t)n_rows * 8, 8)));
+        CK(ctx->stager.h2d(ctx->times.p, row_time_ns, (size_t)n_rows * 8, ctx->stream));
+        ctx->times_ptr = (const int64_t*)ctx->times.p;
+    }
+    ctx->times_rows = n_rows;
+    return TSFX_OK;
+}
+
 static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int max_len, double* d_out, uint32_t flags) {
     const bool timing = (flags & TSFX_FLAG_TIMING) != 0;
     for (int g = 0; g < G_EVENTS; ++g) ctx->ev_used[g] = false;
@@ -573,6 +619,8 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         for (int i = 0; i < nstreams - 1; ++i) CK(cudaStreamWaitEvent(ctx->s_side[i], ctx->ev_fork, 0));
     }
     int launched = 0;
+    bool direct = false;          // the only group wrote the final matrix itself
+    ctx->used_moments = false;
     if (max_len < 1) return fail(ctx, TSFX_E_INVALID, "series of length < 1");
     auto too_long = [&](const char* g) {
         return fail(ctx, TSFX_E_TOO_LONG, std::string("series length ") + std::to_string(max_len) +
@@ -592,6 +640,19 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
         unsigned char* const gs_base = (unsigned char*)ctx->misc.p + (nstreams > 1 ? (size_t)g * slice : 0);
         switch (g) {
             case G_BASIC: {
+                if (P->basic_moments_only) {
+                    // reductions only: stream the series from HBM; with no other group in the plan the rows go
+                    // straight into the caller's matrix (no staging, no assemble pass)
+                    MomentsArgs M;
+                    M.R = R; M.descs = P->dev[g]; M.nd = g_ncols; M.need_high = P->moments_need_high;
+                    direct = (P->n_groups_used == 1) && ctx->peer_out.empty() && (P->ncols == g_ncols);
+                    M.out = direct ? d_final : d_out;
+                    M.ncols = direct ? P->ncols : g_ncols;
+                    M.colmap = direct ? P->d_final_col + P->cum[g] : nullptr;
+                    e = launch_moments(M, gs, ctx->sm_count);
+                    ctx->used_moments = true;
+                    break;
+                }
                 BasicArgs A;
                 A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.lag_needed = P->lag_needed;
@@ -677,7 +738,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
             CK(cudaEventRecord(ctx->ev_join[i], ctx->s_side[i]));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         }
-    {   // scatter the staging matrices into the caller's [n_series x ncols] matrix
+    if (!direct) {   // scatter the staging matrices into the caller's [n_series x ncols] matrix
         if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][0], ctx->stream)); }
         AssembleArgs A;
         A.stage = (const double*)ctx->stage.p; A.out = d_final; A.n_series = R.n_series; A.ncols = P->ncols;
@@ -738,6 +799,8 @@ extern "C" int tsfx_extract_csr(tsfx_ctx* ctx, const tsfx_plan* plan, const floa
     SeriesRef R;
     R.dense_len = 0;
     R.n_series = n_series;
+    rc = take_times(ctx, plan, n_values, &R.times);
+    if (rc) return rc;
     int max_len = 0;
     if (flags & TSFX_FLAG_DEVICE_PTRS) {
         R.values = values; R.begin = begin; R.len = len;
@@ -789,6 +852,10 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
     CK(cudaSetDevice(ctx->device));
     SeriesRef R;
     R.begin = nullptr; R.len = nullptr; R.dense_len = len; R.n_series = n_series;
+    const int64_t* all_times = nullptr;
+    rc = take_times(ctx, plan, n_series * (int64_t)len, &all_times);
+    if (rc) return rc;
+    R.times = all_times;
     if (flags & TSFX_FLAG_DEVICE_PTRS) {
         R.values = values;
         rc = run_groups(ctx, plan, R, len, out, flags);
@@ -816,6 +883,7 @@ extern "C" int tsfx_extract_dense(tsfx_ctx* ctx, const tsfx_plan* plan, const fl
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
         if (check_nan) csr_check_nan(ctx->csr, dv + (size_t)lo * len, cnt * len, ctx->stream);
         R.values = dv + (size_t)lo * len;
+        R.times = all_times ? all_times + (size_t)lo * len : nullptr;
         R.n_series = cnt;
         rc = run_groups(ctx, plan, R, len, dout + (size_t)lo * ncols, flags);
         if (rc) return rc;
@@ -890,7 +958,7 @@ extern "C" int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[g][0], ctx->ev[g][1]));
         if (ms_out) ms_out[k] = ms;
-        if (names_out) names_out[k] = kGroupNames[g];
+        if (names_out) names_out[k] = (g == G_BASIC && ctx->used_moments) ? "moments" : kGroupNames[g];
         ++k;
     }
     return k;
@@ -1017,7 +1085,7 @@ extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sor
 // and are copied to `out` (host) block by block on the D2H stream.
 static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info, const LongIn* stream_in,
                       const int64_t* d_ids, const uint64_t* d_keys, const float* d_vals, bool check_rows, bool check_nan,
-                      double* out, bool out_is_device, uint32_t flags) {
+                      double* out, bool out_is_device, uint32_t flags, const int64_t* row_times = nullptr) {
     CsrWorkspace& W = ctx->csr;
     const size_t ncols = (size_t)plan->ncols;
     const int64_t ns = info.n_series;
@@ -1040,6 +1108,7 @@ static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info,
         if (check_rows) csr_check_rows(W, d_ids, d_keys, stream_in ? stream_in->is_f64 : 0, d_vals, r0, r1, check_nan, ctx->stream);
         SeriesRef R;
         R.values = W.d_values; R.begin = W.d_begin + s0; R.len = W.d_len + s0; R.dense_len = 0; R.n_series = s1 - s0;
+        R.times = row_times;
         int rc = run_groups(ctx, plan, R, info.max_len, dout + (size_t)s0 * ncols, flags);
         if (rc) return rc;
         if (impute || out_is_device) continue;
@@ -1063,10 +1132,13 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn&
     const bool check_nan = !(flags & TSFX_FLAG_NO_NAN_CHECK);
     const int max_blocks = (flags & TSFX_FLAG_TIMING) ? 1 : 16;
     ctx->held_series = -1;
+    const int64_t* times_in = nullptr;           // row timestamps (input row order), device
+    int rc = take_times(ctx, plan, in.n, &times_in);
+    if (rc) return rc;
     CsrInfo info;
     bool streamed = false;
     const int64_t* d_ids; const uint64_t* d_keys; const float* d_vals;
-    int rc = stage_a(ctx, in, max_blocks, check_nan, &info, &streamed, &d_ids, &d_keys, &d_vals);
+    rc = stage_a(ctx, in, max_blocks, check_nan, &info, &streamed, &d_ids, &d_keys, &d_vals);
     if (rc) return rc;
     bool sorted = !info.unsorted_ids;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1091,8 +1163,14 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn&
         }
         if (info.max_len < 1 && ns > 0) return fail(ctx, TSFX_E_INVALID, "empty series");
         const bool first_sorted_try = sorted && attempt == 0;
+        const int64_t* row_times = times_in;
+        if (times_in && W.d_perm) {               // the rows were sorted on the device: the timestamps follow
+            CK(ctx->times_sorted.reserve((size_t)in.n * 8));
+            csr_gather_i64(W, times_in, (int64_t*)ctx->times_sorted.p, in.n, ctx->stream);
+            row_times = (const int64_t*)ctx->times_sorted.p;
+        }
         rc = run_blocks(ctx, plan, info, (first_sorted_try && streamed) ? &in : nullptr, d_ids, d_keys, d_vals,
-                        /*check_rows=*/first_sorted_try && streamed, check_nan, out, in.device, flags);
+                        /*check_rows=*/first_sorted_try && streamed, check_nan, out, in.device, flags, row_times);
         if (rc) return rc;
         if (out_ids) CK(cudaMemcpyAsync(out_ids, W.d_uid, (size_t)ns * sizeof(int64_t), in.device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         if (in.device && !first_sorted_try) break;                       // asynchronous contract: nothing to wait for
@@ -1130,6 +1208,7 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
     if (reuse) {
         if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "the held CSR is extracted into host buffers");
         if (ctx->held_series < 0) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long: no CSR is held by this context");
+        if (plan->need_times) return fail(ctx, TSFX_E_UNSUPPORTED, "linear_trend_timewise: use the one-call form of tsfx_extract_long");
         const int64_t ns = ctx->held_series;
         *n_series_out = ns;
         if (ns == 0) return TSFX_OK;

@@ -24,6 +24,7 @@ struct SeriesRef {              // how a kernel finds its series
     const int32_t* len;         // nullptr => dense
     int32_t dense_len;
     int64_t n_series;
+    const int64_t* times = nullptr;   // optional: timestamp (ns) of every row of `values` (linear_trend_timewise)
 };
 
 __device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }

@@ -159,8 +159,18 @@ static int csr_from_sorted_ids(CsrWorkspace& W, const int64_t* d_ids_sorted, int
     return TSFX_OK;
 }
 
+__global__ void k_gather_i64(const int64_t* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n, int64_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[perm[i]];
+}
+void csr_gather_i64(CsrWorkspace& W, const int64_t* src, int64_t* dst, int64_t n, cudaStream_t st) {
+    if (n > 0 && W.d_perm) k_gather_i64<<<grid_for(n, 256), 256, 0, st>>>(src, W.d_perm, n, dst);
+}
+
 int csr_ids_pass(CsrWorkspace& W, const int64_t* d_ids, int64_t n, int64_t min_block, int max_blocks, cudaStream_t st,
                  std::string* msg) {
+    W.d_perm = nullptr;
     if (n >= (int64_t)1 << 31) { if (msg) *msg = "more than 2^31-1 rows in one call"; return TSFX_E_UNSUPPORTED; }
     CKE(W.init_info(), "alloc info");
     CKE(cudaMemsetAsync(W.d_info, 0, sizeof(CsrInfo), st), "memset info");
@@ -212,6 +222,7 @@ int csr_sort_pass(CsrWorkspace& W, const int64_t* d_ids, const uint64_t* d_keys,
     // gather: sorted ids, sorted values (into pass-A key storage, free by now)
     k_gather_final<<<blocks, threads, 0, st>>>(kb, d_values, perm_out, n, (int64_t*)W.bufs[S_IDS_SORTED], (float*)ka);
     W.d_values = (float*)ka;
+    W.d_perm = perm_out;
     int rc = csr_from_sorted_ids(W, (const int64_t*)W.bufs[S_IDS_SORTED], n, min_block, max_blocks, st, msg);
     if (rc) return rc;
     CKE(cudaMemcpyAsync(W.h_info, W.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, st), "D2H info");

@@ -34,6 +34,7 @@ struct CsrWorkspace {
     int64_t* d_begin = nullptr;
     int32_t* d_len = nullptr;
     float* d_values = nullptr;    // values in (id, sort key) order
+    const uint32_t* d_perm = nullptr;   // after csr_sort_pass: input row of every CSR row (nullptr: rows were in order)
     // internals
     void* bufs[16] = {nullptr};
     size_t caps[16] = {0};
@@ -62,6 +63,9 @@ void csr_check_rows(CsrWorkspace& W, const int64_t* d_ids, const uint64_t* d_key
 // points at the gathered copy), refreshes d_info / h_info (caller synchronises).
 int csr_sort_pass(CsrWorkspace& W, const int64_t* d_ids, const uint64_t* d_keys, int is_f64, const float* d_values,
                   int64_t n_rows, int64_t min_block, int max_blocks, bool check_nan, cudaStream_t st, std::string* msg);
+
+// dst[i] = src[d_perm[i]] (row timestamps follow the sort)
+void csr_gather_i64(CsrWorkspace& W, const int64_t* src, int64_t* dst, int64_t n, cudaStream_t st);
 
 // longest series of a device CSR (synchronises the stream)
 int csr_max_len(CsrWorkspace& W, const int32_t* d_len, int64_t n, cudaStream_t st, int* out);

@@ -115,6 +115,19 @@ cudaError_t launch_basic(const BasicArgs& A, int max_len, cudaStream_t st, int s
 bool basic_finisher_calc(int calc);
 bool sorted_finisher_calc(int calc);    // same for the SORTED group     // host: is this calculator evaluated by the lane-parallel finisher stage?
 
+// reduction-only fast path of the BASIC group (k_moments.cu)
+struct MomentsArgs {
+    SeriesRef R;
+    const Desc* descs;   // device, the BASIC group's descriptors (all moments_only_calc)
+    int nd;
+    double* out;         // staging matrix (colmap == nullptr: column = descriptor index) or the final matrix
+    int ncols;           // row stride of `out`
+    const int32_t* colmap;   // device: final column of descriptor j (direct write, no assemble pass), or nullptr
+    int need_high;       // third / fourth centred moments are needed (skewness, kurtosis)
+};
+cudaError_t launch_moments(const MomentsArgs& A, cudaStream_t st, int sm_count);
+bool moments_only_calc(int calc);       // host: can the reduction-only kernel evaluate this calculator?
+
 struct SortedArgs {
     SeriesRef R;
     unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used

@@ -278,8 +278,10 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             continue
         dp = _device_plan(ctx, plan)
         v32 = values.to_numpy().astype(np.float32, copy=False)
+        # linear_trend_timewise regresses on the rows' DatetimeIndex (feature_calculators.py:2296-2299)
+        times = values.index.as_unit("ns").asi8 if plan.needs_times else None
         try:
-            uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags)
+            uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags, times=times)
         except ValueError as e:
             if "contains NaN" in str(e):          # TSFX_E_NAN: the check of data.py:148-167, done on the device
                 raise ValueError("Column must not contain NaN values: {}".format(value_name)) from None

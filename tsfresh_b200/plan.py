@@ -169,6 +169,7 @@ class Plan:
         rows = []                   # dict(calc, attr, i0, i1, i2, p0, p1) per column
         self.cwt_scales = []        # distinct cwt scales -> table index
         self.skipped = []           # calculators skipped with a warning (DatetimeIndex required)
+        self.needs_times = False    # linear_trend_timewise columns: the extract call needs the rows' timestamps
         for key, plist in fc_parameters.items():
             if callable(key):
                 _unsupported(getattr(key, "__name__", repr(key)), "a user-supplied callable calculator")
@@ -316,9 +317,12 @@ class Plan:
             yield "num_segments_%s__segment_focus_%s" % (p["num_segments"], p["segment_focus"]), dict(
                 b, calc=CALC["TSFX_ENERGY_RATIO_BY_CHUNKS"], i0=ns, i1=sf)
 
-    def _c_linear_trend_timewise(self, plist, b):  # :2302 (only reached with a DatetimeIndex)
-        _unsupported("linear_trend_timewise", "a DatetimeIndex-based regression")
-        yield  # pragma: no cover
+    def _c_linear_trend_timewise(self, plist, b):  # :2302-2305 (only reached with a DatetimeIndex)
+        self.needs_times = True
+        for p in plist:
+            if p["attr"] not in LR_ATTR:
+                _unsupported("linear_trend_timewise", "attr=%r" % (p["attr"],))
+            yield 'attr_"%s"' % p["attr"], dict(b, calc=CALC["TSFX_LINEAR_TREND_TIMEWISE"], attr=LR_ATTR[p["attr"]])
 
     def _c_query_similarity_count(self, plist, b):  # :2505-2519
         for p in plist:
