@@ -24,7 +24,7 @@ def to_csr(series):
     return values, begin, lens
 
 
-def gpu_vs_oracle(ctx, settings, series, rtol=1e-5):
+def gpu_vs_oracle(ctx, settings, series, rtol=1e-5, atol=0.0):
     """Runs `settings` over the list of float32 series on the GPU (C-ABI, CSR path) and in the oracle;
     returns (mismatches, plan, gpu_matrix, oracle_matrix)."""
     from tsfresh_b200._lib import DevicePlan
@@ -36,4 +36,4 @@ def gpu_vs_oracle(ctx, settings, series, rtol=1e-5):
     finally:
         dp.close()
     want = oracle_rows([np.asarray(s, dtype=np.float32).astype(np.float64) for s in series], settings)
-    return compare(got, want, plan.suffixes, rtol=rtol), plan, got, want
+    return compare(got, want, plan.suffixes, rtol=rtol, atol=atol), plan, got, want

@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from oracle.extract import compare, oracle_rows
+from oracle.extract import NOISE_FLOOR, compare, oracle_rows
 from tests.helpers import synthetic_series
 from tsfresh_b200 import EfficientFCParameters, MinimalFCParameters, extract_features
 from tsfresh_b200.plan import Plan
@@ -29,7 +29,7 @@ def check(X, series, settings, prefix="value__"):
     plan = Plan(settings)
     assert list(X.columns) == [prefix + s for s in plan.suffixes]
     want = oracle_rows([np.asarray(s, np.float32).astype(np.float64) for s in series], settings)
-    bad = compare(X.to_numpy(), want, plan.suffixes)
+    bad = compare(X.to_numpy(), want, plan.suffixes, atol=NOISE_FLOOR)     # these frames hold 1- and 2-sample series
     assert not bad, bad[:20]
 
 
@@ -231,10 +231,29 @@ def test_linear_trend_timewise_on_a_datetime_index():
         X = extract_features(frame, column_id="id", default_fc_parameters=fc)
         assert list(X.columns) == list(z["columns"]) and list(X.index) == list(z["index"])
         suffixes = [c.split("__", 1)[1] for c in X.columns]
-        bad = compare(X.to_numpy(), z["reference"], suffixes)
+        bad = compare(X.to_numpy(), z["reference"], suffixes, atol=NOISE_FLOOR)     # 2- and 3-sample series
         assert not bad, bad[:20]
     plain = df.reset_index(drop=True)
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         X = extract_features(plain, column_id="id", default_fc_parameters=fc, show_warnings=True)
     assert [c for c in X.columns if "timewise" in c] == [] and any("DatetimeIndex" in str(m.message) for m in w)
+
+
+def test_do_extraction_on_chunk_signature():
+    """the per-(id, kind) function of the dask / spark bindings (extraction.py:308-386, bindings.py:50-54)"""
+    from tsfresh_b200 import _do_extraction_on_chunk, do_extraction_on_chunks
+    rng = np.random.default_rng(21)
+    x = pd.Series(rng.standard_normal(100).astype(np.float32))
+    s = MinimalFCParameters()
+    triples = _do_extraction_on_chunk((7, "a", x), default_fc_parameters=s, kind_to_fc_parameters={})
+    plan = Plan(s)
+    assert [t[0] for t in triples] == [7] * plan.n_cols and [t[1] for t in triples] == ["a__" + c for c in plan.suffixes]
+    want = oracle_rows([x.to_numpy(np.float64)], s)
+    assert not compare(np.array([[t[2] for t in triples]]), want, plan.suffixes)
+    # batched: two kinds with their own settings, order of the triples = order of the chunks
+    y = pd.Series(rng.standard_normal(40).astype(np.float32))
+    out = do_extraction_on_chunks([(1, "a", x), (1, "b", y), (2, "a", y)], s, {"b": {"maximum": None, "minimum": None}})
+    assert [t[:2] for t in out[:plan.n_cols]] == [(1, "a__" + c) for c in plan.suffixes]
+    assert out[plan.n_cols:plan.n_cols + 2] == [(1, "b__maximum", float(y.max())), (1, "b__minimum", float(y.min()))]
+    assert len(out) == 2 * plan.n_cols + 2

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from oracle.extract import NOISE_FLOOR
 from tests.helpers import gpu_vs_oracle, synthetic_series
 from tsfresh_b200.settings import ComprehensiveFCParameters, MinimalFCParameters
 
@@ -42,7 +43,8 @@ def _report(bad):
 @pytest.mark.parametrize("length", [256, 100, 1024, 37])
 def test_basic_group(ctx, kind, length):
     series = list(synthetic_series(7 + length, 48, length, kind))
-    bad, plan, got, want = gpu_vs_oracle(ctx, basic_settings(), series)
+    # "rounded" series are multiples of 0.5: sums that are exactly 0 occur, the reference returns rounding noise there
+    bad, plan, got, want = gpu_vs_oracle(ctx, basic_settings(), series, atol=NOISE_FLOOR if kind == "rounded" else 0.0)
     assert not bad, _report(bad)
 
 
@@ -60,5 +62,5 @@ def test_short_and_ragged(ctx):
     series = [rng.standard_normal(n).astype(np.float32) for n in (1, 2, 3, 4, 5, 8, 20, 31, 32, 33, 63, 64, 65, 200, 1500)]
     series += [np.zeros(10, np.float32), np.ones(7, np.float32), np.array([1, 1, 2, 2, 3, 3, 3], np.float32),
                np.array([5.0], np.float32), np.array([-1, 1] * 20, np.float32)]
-    bad, *_ = gpu_vs_oracle(ctx, basic_settings(), series)
+    bad, *_ = gpu_vs_oracle(ctx, basic_settings(), series, atol=NOISE_FLOOR)        # constant / alternating / 1-sample series
     assert not bad, _report(bad)

@@ -7,7 +7,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from oracle.extract import compare
+from oracle.extract import NOISE_FLOOR, compare
 from tsfresh_b200 import ComprehensiveFCParameters, EfficientFCParameters, extract_features
 from tsfresh_b200.plan import Plan
 
@@ -24,7 +24,7 @@ def test_comprehensive_matches_reference_golden():
     got = dp.extract_csr(z["values"], z["begin"], z["length"])
     dp.close()
     ctx.close()
-    bad = compare(got, z["reference"], plan.suffixes)
+    bad = compare(got, z["reference"], plan.suffixes, atol=NOISE_FLOOR)         # ragged fixture incl. 1..5-sample and constant series
     assert not bad, bad[:30]
 
 
@@ -35,7 +35,7 @@ def test_fixture80_through_extract_features():
                          default_fc_parameters=EfficientFCParameters())
     assert list(X.columns) == list(z["columns"]) and list(X.index) == list(z["index"])
     suffixes = [c.split("__", 1)[1] for c in X.columns]
-    bad = compare(X.to_numpy(), z["reference"], suffixes)
+    bad = compare(X.to_numpy(), z["reference"], suffixes, atol=NOISE_FLOOR)     # 20 small integers per series
     # the fixture is 20 small integers per series: many exact ties.  permutation_entropy on tied windows is
     # implementation-defined in the reference (numpy's default argsort is unstable)
     bad = [b for b in bad if not b[1].startswith("permutation_entropy")]

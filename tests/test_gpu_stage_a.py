@@ -143,11 +143,12 @@ def test_device_pointers(env):
 
 def test_pinned_pool_reuses_blocks(env):
     ctx, dp, plan = env
-    a = ctx.pinned_array((1000, 10), np.float64)
+    shape = (12345, 77)                                   # a size no other test has left in the pool
+    a = ctx.pinned_array(shape, np.float64)
     addr = a.ctypes.data
     a[:] = 1.0
     del a
     import gc
     gc.collect()
-    b = ctx.pinned_array((1000, 10), np.float64)
+    b = ctx.pinned_array(shape, np.float64)
     assert b.ctypes.data == addr                          # the freed block came back from the pool

@@ -142,6 +142,54 @@ __device__ __forceinline__ void lag_products(const double* xc, int n, int kmax, 
     }
 }
 
+// The same lag products on the FP64 tensor cores (mma.sync m8n8k4, DMMA) -- the one GEMM-shaped piece of the path
+// (BASELINE.json north_star).  With A[i][u] = xc[8 (b + u) + i] and B[u][j] = xc[8 (b + t + u) + j] (b = sample block,
+// t = tile) the accumulator D_t[i][j] = sum_b,u A B collects x[s] x[s + 8 t + j - i] over all s = i mod 8: tile t
+// holds lags 8 t - 7 .. 8 t + 7 on its diagonals, every (lag, residue) pair lands in exactly one tile, and
+// lagS[k] = sum of the diagonal j - i = k - 8 t over the tiles.  Both fragments are the same strided view of xc
+// (zero beyond n), so one shared-memory load feeds each MMA: per series ~8 loads + 6 MMAs per 32 samples and one
+// diagonal fold per tile, instead of 41 x (8 loads + 8 FMAs + a warp sum) per 256 samples.
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#define TSFX_DMMA_MAX_TILES 8
+__device__ __forceinline__ void lag_products_dmma(const double* xc, int n, int kmax, int ntiles, double* lagS, double* tile,
+                                                  int lane) {
+    double acc[TSFX_DMMA_MAX_TILES][2];
+#pragma unroll
+    for (int t = 0; t < TSFX_DMMA_MAX_TILES; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    const int li = lane >> 2, lu = lane & 3;
+    const int G = (n + 31) >> 5;                          // groups of 4 sample blocks (32 samples)
+    const double* xl = xc + 8 * lu + li;
+    for (int g = 0; g < G; ++g) {
+        const double a = xl[32 * g];
+#pragma unroll
+        for (int t = 0; t < TSFX_DMMA_MAX_TILES; ++t)
+            if (t < ntiles) dmma_884(acc[t][0], acc[t][1], a, xl[32 * g + 8 * t]);
+    }
+    for (int k = lane; k <= kmax; k += 32) lagS[k] = 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < TSFX_DMMA_MAX_TILES; ++t) {
+        if (t < ntiles) {
+            tile[li * 8 + 2 * lu] = acc[t][0];            // D[i][j]: i = lane / 4, j = 2 (lane % 4) + {0, 1}
+            tile[li * 8 + 2 * lu + 1] = acc[t][1];
+            __syncwarp();
+            if (lane < 15) {
+                const int d = lane - 7, k = 8 * t + d;    // diagonal j - i = d of tile t = lag k
+                if (k >= 0 && k <= kmax) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int j = i + d; if (j >= 0 && j < 8) sum += tile[i * 8 + j]; }
+                    lagS[k] += sum;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // numpy histogram bin index for uniform bins (numpy/lib/_histograms_impl.py fast path)
 __device__ __forceinline__ int hist_bin(double v, double first, double last, double denom, double step, int nb) {
     double f = __dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), (double)nb);
@@ -353,7 +401,13 @@ template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
+    // the descriptor table is walked by every warp on every trip: one copy per CTA in shared memory (the global-memory
+    // fetch of the next descriptor right after the trip's barrier was the hottest line of the kernel)
+    Desc* sdesc = reinterpret_cast<Desc*>(smem_raw);
+    for (int i = threadIdx.x; i < A.nd * (int)(sizeof(Desc) / 8); i += WPC * 32)
+        reinterpret_cast<double*>(sdesc)[i] = reinterpret_cast<const double*>(A.descs)[i];
+    __syncthreads();
+    unsigned char* base = warp_region<GS>(smem_raw + A.desc_bytes, A.gscratch, A.bytes_per_warp, WPC, warp);
     double* xc = reinterpret_cast<double*>(base);
     double* scr = xc + A.nxc;
     double* lagS = scr + A.nscr;
@@ -379,7 +433,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
         for (int i = n + lane; i < A.nxc; i += 32) xc[i] = 0.0;
         __syncwarp();
         if (A.lag_needed > 0) {         // lag products 0..min(lag_needed, n-1)
-            lag_products(xc, n, min(A.lag_needed, n - 1), lagS, lane);
+            if (A.lag_tiles > 0) lag_products_dmma(xc, n, min(A.lag_needed, n - 1), A.lag_tiles, lagS, scr, lane);
+            else lag_products(xc, n, min(A.lag_needed, n - 1), lagS, lane);
             __syncwarp();
         }
         if (lane == 0) {
@@ -397,7 +452,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
         // finishers (the first A.nfin descriptors of the group): one descriptor per lane
         if (live)
             for (int j = lane; j < A.nfin; j += 32) {
-                const Desc d = A.descs[j];
+                const Desc d = sdesc[j];
                 orow[d.col] = basic_finisher(d, ST, lagS);
             }
         // The remaining descriptors are sorted by calculator (tsfx_plan_create) and descriptor j writes column j of
@@ -406,11 +461,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
         // when the per-descriptor work is O(1) after a shared preparation (then one descriptor per lane).
         for (int j = A.nfin; j < A.nd;) {
             if (WPC > 1) __syncthreads();
-            const Desc d = A.descs[j];
+            const Desc d = sdesc[j];
             int run = 0;                    // descriptors j .. j+run-1 have the same calculator
             for (;;) {
                 const int jj = j + run + lane;
-                const unsigned same = __ballot_sync(FULL, jj < A.nd && A.descs[jj].calc == d.calc);
+                const unsigned same = __ballot_sync(FULL, jj < A.nd && sdesc[jj].calc == d.calc);
                 if (same == FULL) { run += 32; continue; }
                 run += __ffs(~same) - 1;
                 break;
@@ -426,7 +481,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     double thr[NB];
                     int c[NB];
 #pragma unroll
-                    for (int t = 0; t < NB; ++t) { thr[t] = t < used ? A.descs[j + t].p0 * M.sd : dinf(); c[t] = 0; }
+                    for (int t = 0; t < NB; ++t) { thr[t] = t < used ? sdesc[j + t].p0 * M.sd : dinf(); c[t] = 0; }
                     for (int i = lane; i < n; i += 32) {
                         const double v = fabs(xc[i]);
 #pragma unroll
@@ -489,7 +544,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     unsigned char* rad = reinterpret_cast<unsigned char*>(scr);
                     int* cand = reinterpret_cast<int*>(rad + ((n + 3) & ~3));
                     int supmax = 1;
-                    for (int t = lane; t < run; t += 32) supmax = max(supmax, A.descs[j + t].i0);
+                    for (int t = lane; t < run; t += 32) supmax = max(supmax, sdesc[j + t].i0);
                     supmax = min(wmaxi(supmax), 255);
                     int ncand = 0;
                     for (int b0 = 0; b0 < n; b0 += 32) {
@@ -523,7 +578,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     for (int t0 = 0; t0 < run; t0 += NB) {
                         int sup[NB], c[NB];
 #pragma unroll
-                        for (int t = 0; t < NB; ++t) { sup[t] = (t0 + t < run) ? A.descs[j + t0 + t].i0 : 0x7fffffff; c[t] = 0; }
+                        for (int t = 0; t < NB; ++t) { sup[t] = (t0 + t < run) ? sdesc[j + t0 + t].i0 : 0x7fffffff; c[t] = 0; }
                         for (int i = lane; i < n; i += 32) {
                             const int rv = rad[i];
 #pragma unroll
@@ -608,7 +663,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     }
                     __syncwarp();
                     if (live)
-                        for (int t = lane; t < run; t += 32) orow[j + t] = pac[A.descs[j + t].i0];
+                        for (int t = lane; t < run; t += 32) orow[j + t] = pac[sdesc[j + t].i0];
                     break;
                 }
                 case TSFX_TIME_REVERSAL_ASYMMETRY_STATISTIC: {
@@ -658,7 +713,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                         double qv[NB];
                         int c[NB];
 #pragma unroll
-                        for (int t = 0; t < NB; ++t) { qv[t] = (t0 + t < run) ? A.descs[j + t0 + t].p0 : 0.0; c[t] = 0; }
+                        for (int t = 0; t < NB; ++t) { qv[t] = (t0 + t < run) ? sdesc[j + t0 + t].p0 : 0.0; c[t] = 0; }
                         for (int i = lane; i < n; i += 32) {
                             const double f = scr[i];
 #pragma unroll
@@ -679,7 +734,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     used = run;                                         // one segment per lane
                     stored = true;
                     for (int t = lane; t < run; t += 32) {
-                        const Desc e = A.descs[j + t];
+                        const Desc e = sdesc[j + t];
                         double rr = dnan();
                         if (M.sumsq != 0.0) {
                             const int ns = e.i0, fo = e.i1;
@@ -712,7 +767,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     sxy = wsum(sxy) / dn;
                     const LinReg fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
                     if (live)
-                        for (int t = lane; t < run; t += 32) orow[j + t] = m_linreg_pick(fit, A.descs[j + t].attr);
+                        for (int t = lane; t < run; t += 32) orow[j + t] = m_linreg_pick(fit, sdesc[j + t].attr);
                     break;
                 }
                 case TSFX_LINEAR_TREND_TIMEWISE: {
@@ -744,7 +799,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                         fit = m_linregress(dn, tm, M.mean, sxx, M.var, sxy);
                     }
                     if (live)
-                        for (int t = lane; t < run; t += 32) orow[j + t] = have ? m_linreg_pick(fit, A.descs[j + t].attr) : dnan();
+                        for (int t = lane; t < run; t += 32) orow[j + t] = have ? m_linreg_pick(fit, sdesc[j + t].attr) : dnan();
                     break;
                 }
                 case TSFX_AGG_LINEAR_TREND: {
@@ -754,7 +809,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     stored = true;
                     int slot = 0, key_prev = -1;
                     for (int t = 0; t < run; ++t) {
-                        const int cl = A.descs[j + t].i0, fa = A.descs[j + t].i1;
+                        const int cl = sdesc[j + t].i0, fa = sdesc[j + t].i1;
                         const int key = (cl << 4) | fa;
                         if (key == key_prev) continue;
                         key_prev = key;
@@ -779,7 +834,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArg
                     for (int t0 = 0; t0 < run; t0 += 32) {
                         const int t = t0 + lane;
                         const bool ok = t < run;
-                        const Desc e = A.descs[j + (ok ? t : 0)];
+                        const Desc e = sdesc[j + (ok ? t : 0)];
                         const int key = (e.i0 << 4) | e.i1;
                         int prev = __shfl_up_sync(FULL, key, 1);
                         if (lane == 0) prev = last_key;
@@ -840,12 +895,27 @@ cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int 
     BasicArgs A = A0;
     A.npad = (max_len + 3) & ~3;
     A.nxc = ((max_len + 255) / 256) * 256 + ((A.lag_needed + 1) & ~1);      // centred copy + zero tail for the lag products
+    {
+        // lag products on the FP64 tensor cores (DMMA) unless TSFX_LAG=fma or the largest lag needs more than 8 tiles
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("TSFX_LAG"); mode = (e && e[0] == 'f') ? 0 : 1; }
+        const int tiles = A.lag_needed / 8 + 1 + ((A.lag_needed & 7) ? 1 : 0);
+        A.lag_tiles = (mode == 1 && A.lag_needed > 0 && tiles <= TSFX_DMMA_MAX_TILES) ? tiles : 0;
+        if (A.lag_tiles > 0) {     // the strided fragment loads read up to 32 ceil(n / 32) + 8 tiles + 24 samples
+            const int need = ((max_len + 31) / 32) * 32 + 8 * A.lag_tiles + 32;
+            if (A.nxc < need) A.nxc = (need + 1) & ~1;
+        }
+    }
     size_t per = (size_t)A.nxc * 8 + (size_t)A.nscr * 8 + (size_t)A.nlag * 8 + 32 * 8 + (size_t)A.nalt * 48 + (size_t)A.npad * 4;
     per = (per + 15) & ~(size_t)15;
     A.bytes_per_warp = (int)per;
+    A.desc_bytes = (int)(((size_t)A.nd * sizeof(Desc) + 15) & ~(size_t)15);
     Geometry G;
-    if (!plan_geometry(per, 100 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
+    const size_t budget = (size_t)100 * 1024 > (size_t)A.desc_bytes + per ? (size_t)100 * 1024 - A.desc_bytes : per;
+    if (!plan_geometry(per, budget, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
     A.gscratch = G.gscratch;
+    G.smem += A.desc_bytes;                       // CTA-wide descriptor table in front of the per-warp regions
+    if (G.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     TSFX_DISPATCH(k_basic, G, st, A)
     return cudaGetLastError();
 }

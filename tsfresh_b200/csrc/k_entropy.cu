@@ -229,15 +229,16 @@ __device__ __forceinline__ float key_f32(unsigned k) {
 
 struct RankLayout {            // byte offsets inside one series' working region
     int t_off, s_off, pi_off, rk_off, lh_off, cnt_off, red_off, bytes;
-    int rs;                    // row stride of T in 32-bit words (multiple of 4, odd multiple of 16 bytes)
+    int lh_stride;             // words between the two interval tables
+    int rs;                    // row stride of T in 32-bit words (multiple of 4; padded to an odd multiple of 16 bytes when pad != 0)
 };
-__host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
+__host__ __device__ inline RankLayout rank_layout(int nmax, int G, int pad) {
     RankLayout L;
     int n2 = 32;
     while (n2 < nmax) n2 <<= 1;
     const int W = (nmax + 31) >> 5;
     int rs4 = (W + 3) >> 2;
-    if ((rs4 & 1) == 0) rs4 += 1;
+    if (pad && (rs4 & 1) == 0) rs4 += 1;
     L.rs = rs4 * 4;
     int tb = (nmax + 1) * L.rs * 4;
     if (tb < n2 * 8) tb = n2 * 8;                  // the sort keys alias the table
@@ -246,7 +247,9 @@ __host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
     L.s_off = o; o += (n2 * 4 + 15) & ~15;                     // sorted keys (uint32), 0xffffffff beyond n
     L.pi_off = o; o += (n2 * 2 + 15) & ~15;
     L.rk_off = o; o += ((nmax + 2) * 2 + 15) & ~15;
-    L.lh_off = o; o += (((nmax + 3) & ~3) * 4 + 15) & ~15;   // lo | (hi+1) << 16 per rank; aliases the float32 staging copy
+    L.lh_stride = (nmax + 3) & ~3;
+    L.lh_off = o; o += 2 * ((L.lh_stride * 4 + 15) & ~15);    // two tables of lo | (hi+1) << 16 per rank; the first aliases the float32 staging copy
+    L.lh_stride = ((L.lh_stride * 4 + 15) & ~15) / 4;
     L.cnt_off = o; o += ((nmax + 2) * 4 + 15) & ~15;           // histogram of the interval starts
     L.red_off = o; o += (G > 1) ? G * 4 * 8 : 0;
     L.bytes = (o + 15) & ~15;
@@ -254,14 +257,14 @@ __host__ __device__ inline RankLayout rank_layout(int nmax, int G) {
 }
 
 template <int G, int SPC>
-__global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1))) k_entropy_rank(EntropyArgs A) {
+__global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1))) k_entropy_rank(EntropyArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NTHR = G * 32;
     const int lane = threadIdx.x & 31;
     const int grp = threadIdx.x / NTHR;                 // series slot inside the CTA
     const int tid = threadIdx.x - grp * NTHR;           // thread inside the series group
     const int gw = tid >> 5;                            // warp inside the series group
-    const RankLayout L = rank_layout(A.npad, G);
+    const RankLayout L = rank_layout(A.npad, G, A.rank_pad);
     double* lnk = reinterpret_cast<double*>(smem_raw);                              // log(k), k = 0..npad (CTA-wide)
     unsigned char* base = smem_raw + (((A.npad + 1) * 8 + 15) & ~15) + (size_t)grp * L.bytes;
     unsigned* T = reinterpret_cast<unsigned*>(base + L.t_off);
@@ -361,122 +364,167 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 3 : (G == 4 ? 4 : 1)))
         gsync<G>();
         double* orow = A.out + (size_t)s * A.ncols;
         const int n2 = n - 1, n3 = n - 2;
-        for (int dj = 0; dj < A.nd; ++dj) {
-            const Desc d = A.descs[dj];
-            const double tau = (d.calc == TSFX_SAMPLE_ENTROPY) ? 0.2 * M.sd : d.p0 * M.sd;
-            const bool sane = tau >= 0.0;                    // NaN / negative tolerance: every comparison is false
-            // ---- phase A: rank interval [lo, hi] of every rank r.
+        // tolerances are processed two at a time: the two interval tables are built one after the other, then ONE sweep
+        // over the row blocks counts both (two independent dependency chains per lane hide the shuffle / load latency)
+        for (int dj = 0; dj < A.nd; dj += 2) {
+            const int nq = min(2, A.nd - dj);
+            double tauq[2];
+            for (int q = 0; q < 2; ++q) {
+                const Desc d = A.descs[dj + (q < nq ? q : 0)];
+                tauq[q] = (d.calc == TSFX_SAMPLE_ENTROPY) ? 0.2 * M.sd : d.p0 * M.sd;
+            }
+            // ---- phase A: rank interval [lo, hi] of every rank r, per tolerance.
             // lo(r) = #{ a : x_(a) < L_r } where L_r is the smallest float32 y with fl64(x_(r) - y) <= tau (the predicate is
             // monotone in y, so the interval is exact): L_r = round-up of x_(r) - tau, corrected by at most one float32
             // step with the exact predicate, then ONE binary search over the sorted keys.  hi needs no second search:
             // the relation is symmetric (a <= hi(r) <=> lo(a) <= r), so hi(r) + 1 = #{ a : lo(a) <= r } = the inclusive
             // prefix sum of the histogram of lo.
-            for (int r = tid; r <= n; r += NTHR) cnt[r] = 0u;
-            gsync<G>();
-            if (sane) {
-                constexpr int U = 4;                                 // ranks per lane in flight (independent chains)
-                for (int r0 = tid; r0 < n; r0 += U * NTHR) {
-                    unsigned kL[U];
-                    int pos[U];
+            for (int q = 0; q < nq; ++q) {
+                unsigned* lh = lohi + (size_t)q * L.lh_stride;
+                const double tau = tauq[q];
+                const bool sane = tau >= 0.0;                    // NaN / negative tolerance: every comparison is false
+                for (int r = tid; r <= n; r += NTHR) cnt[r] = 0u;
+                gsync<G>();
+                if (sane) {
+                    constexpr int U = 4;                                 // ranks per lane in flight (independent chains)
+                    for (int r0 = tid; r0 < n; r0 += U * NTHR) {
+                        unsigned kL[U];
+                        int pos[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int r = r0 + u * NTHR;
-                        const double sr = (double)key_f32(sk[r < n ? r : 0]);
-                        float Lf = __double2float_ru(sr - tau);
-                        if (!((sr - (double)Lf) <= tau)) Lf = key_f32(f32_key(Lf) + 1u);       // one float32 step up
-                        else {
-                            const float Lp = key_f32(f32_key(Lf) - 1u);                          // one step down still inside?
-                            if ((sr - (double)Lp) <= tau) Lf = Lp;
+                        for (int u = 0; u < U; ++u) {
+                            const int r = r0 + u * NTHR;
+                            const double sr = (double)key_f32(sk[r < n ? r : 0]);
+                            float Lf = __double2float_ru(sr - tau);
+                            if (!((sr - (double)Lf) <= tau)) Lf = key_f32(f32_key(Lf) + 1u);       // one float32 step up
+                            else {
+                                const float Lp = key_f32(f32_key(Lf) - 1u);                          // one step down still inside?
+                                if ((sr - (double)Lp) <= tau) Lf = Lp;
+                            }
+                            kL[u] = f32_key(Lf);
+                            pos[u] = 0;
                         }
-                        kL[u] = f32_key(Lf);
-                        pos[u] = 0;
-                    }
-                    for (int st = N2 >> 1; st > 0; st >>= 1) {
+                        for (int st = N2 >> 1; st > 0; st >>= 1) {
 #pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            if (sk[pos[u] + st - 1] < kL[u]) pos[u] += st;
-                    }
+                            for (int u = 0; u < U; ++u)
+                                if (sk[pos[u] + st - 1] < kL[u]) pos[u] += st;
+                        }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int r = r0 + u * NTHR;
+                        for (int u = 0; u < U; ++u) {
+                            const int r = r0 + u * NTHR;
+                            if (r < n) {
+                                // (N2 a power of two >= n: the search above covers [0, N2 - 1]; a count of N2 - 1 can only
+                                // be short by the last element, checked here)
+                                int lo = pos[u];
+                                if (lo == N2 - 1 && sk[N2 - 1] < kL[u]) lo = N2;
+                                lh[r] = (unsigned)lo;
+                                atomicAdd(&cnt[lo], 1u);
+                            }
+                        }
+                    }
+                }
+                gsync<G>();
+                if (gw == 0) {          // inclusive scan of the histogram by one warp: lane l owns a contiguous run of ranks
+                    const int run = (n + 31) >> 5;
+                    const int b0 = lane * run;
+                    unsigned tot = 0u;
+                    for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
+                    unsigned inc = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+                    unsigned acc = inc - tot;
+                    for (int k = 0; k < run; ++k) {
+                        const int r = b0 + k;
                         if (r < n) {
-                            // (N2 a power of two >= n: the search above covers [0, N2 - 1]; a count of N2 - 1 < n can only
-                            // be short by the last element, checked here)
-                            int lo = pos[u];
-                            if (lo == N2 - 1 && sk[N2 - 1] < kL[u]) lo = N2;
-                            lohi[r] = (unsigned)lo;
-                            atomicAdd(&cnt[lo], 1u);
+                            acc += cnt[r];
+                            lh[r] = sane ? (lh[r] | (acc << 16)) : 0x00010001u;       // lo | (hi + 1) << 16; empty: T[1] & ~T[1]
                         }
                     }
                 }
+                gsync<G>();
             }
-            gsync<G>();
-            if (gw == 0) {              // inclusive scan of the histogram by one warp: lane l owns a contiguous run of ranks
-                const int run = (n + 31) >> 5;
-                const int b0 = lane * run;
-                unsigned tot = 0u;
-                for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
-                unsigned inc = tot;
+            // ---- phase B: template counts, lane = row (30 rows per block: rows i+1, i+2 come from the next lanes)
+            double l2[2] = {0.0, 0.0}, l3[2] = {0.0, 0.0};
+            int iB[2] = {0, 0}, iA[2] = {0, 0};
+            const unsigned* lh1 = lohi + (nq > 1 ? L.lh_stride : 0);
+#define TSFX_RANK_STEP(Q, WN)                                                                  \
+            {                                                                                  \
+                const unsigned wn_ = (WN);                                                     \
+                const unsigned s1n = __shfl_down_sync(FULL, wn_, 1), s2n = __shfl_down_sync(FULL, wn_, 2); \
+                const unsigned m2 = wp[Q] & __funnelshift_r(s1p[Q], s1n, 1);                   \
+                const unsigned m3 = m2 & __funnelshift_r(s2p[Q], s2n, 2);                      \
+                c2[Q] += __popc(m2);                                                           \
+                c3[Q] += __popc(m3);                                                           \
+                wp[Q] = wn_; s1p[Q] = s1n; s2p[Q] = s2n;                                       \
+            }
+            auto sweep = [&](auto nc_tag) {
+                constexpr int NC = decltype(nc_tag)::value;          // 16-byte chunks per row, 0 = run-time count
+                const int nchunks = NC > 0 ? NC : (Wr >> 2);
+                for (int r0 = gw * 30; r0 < n2; r0 += G * 30) {
+                    const int i = r0 + lane;
+                    const int ri = i < n ? (int)rk[i] : 0;
+                    const unsigned lhA = i < n ? lohi[ri] : 0x00010001u;
+                    const unsigned lhB = i < n ? lh1[ri] : 0x00010001u;
+                    const uint4* ThiA = reinterpret_cast<const uint4*>(T + (size_t)(lhA >> 16) * RS);
+                    const uint4* TloA = reinterpret_cast<const uint4*>(T + (size_t)(lhA & 0xffffu) * RS);
+                    const uint4* ThiB = reinterpret_cast<const uint4*>(T + (size_t)(lhB >> 16) * RS);
+                    const uint4* TloB = reinterpret_cast<const uint4*>(T + (size_t)(lhB & 0xffffu) * RS);
+                    unsigned wp[2] = {0u, 0u}, s1p[2] = {0u, 0u}, s2p[2] = {0u, 0u};
+                    int c2[2] = {0, 0}, c3[2] = {0, 0};
+                    if (NC > 0) {
+                        uint4 hA[NC > 0 ? NC : 1], lA[NC > 0 ? NC : 1], hB[NC > 0 ? NC : 1], lB[NC > 0 ? NC : 1];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-                unsigned acc = inc - tot;
-                for (int k = 0; k < run; ++k) {
-                    const int r = b0 + k;
-                    if (r < n) {
-                        acc += cnt[r];
-                        lohi[r] = sane ? (lohi[r] | (acc << 16)) : 0x00010001u;       // lo | (hi + 1) << 16; empty: T[1] & ~T[1]
+                        for (int c = 0; c < NC; ++c) { hA[c] = ThiA[c]; lA[c] = TloA[c]; hB[c] = ThiB[c]; lB[c] = TloB[c]; }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            TSFX_RANK_STEP(0, hA[c].x & ~lA[c].x) TSFX_RANK_STEP(1, hB[c].x & ~lB[c].x)
+                            TSFX_RANK_STEP(0, hA[c].y & ~lA[c].y) TSFX_RANK_STEP(1, hB[c].y & ~lB[c].y)
+                            TSFX_RANK_STEP(0, hA[c].z & ~lA[c].z) TSFX_RANK_STEP(1, hB[c].z & ~lB[c].z)
+                            TSFX_RANK_STEP(0, hA[c].w & ~lA[c].w) TSFX_RANK_STEP(1, hB[c].w & ~lB[c].w)
+                        }
+                    } else {
+                        for (int c = 0; c < nchunks; ++c) {
+                            const uint4 hA = ThiA[c], lA = TloA[c], hB = ThiB[c], lB = TloB[c];
+                            TSFX_RANK_STEP(0, hA.x & ~lA.x) TSFX_RANK_STEP(1, hB.x & ~lB.x)
+                            TSFX_RANK_STEP(0, hA.y & ~lA.y) TSFX_RANK_STEP(1, hB.y & ~lB.y)
+                            TSFX_RANK_STEP(0, hA.z & ~lA.z) TSFX_RANK_STEP(1, hB.z & ~lB.z)
+                            TSFX_RANK_STEP(0, hA.w & ~lA.w) TSFX_RANK_STEP(1, hB.w & ~lB.w)
+                        }
+                    }
+                    TSFX_RANK_STEP(0, 0u) TSFX_RANK_STEP(1, 0u)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (lane < 30 && i < n2) { l2[q] += lnk[c2[q]]; iB[q] += c2[q] - 1; }
+                        if (lane < 30 && i < n3) { l3[q] += lnk[c3[q]]; iA[q] += c3[q] - 1; }
                     }
                 }
-            }
-            gsync<G>();
-            // ---- phase B: template counts, lane = row (30 rows per block: rows i+1, i+2 come from the next lanes)
-            double l2 = 0.0, l3 = 0.0;
-            int iB = 0, iA = 0;
-            for (int r0 = gw * 30; r0 < n2; r0 += G * 30) {
-                const int i = r0 + lane;
-                const unsigned lh = i < n ? lohi[rk[i]] : 0x00010001u;
-                const uint4* Thi = reinterpret_cast<const uint4*>(T + (size_t)(lh >> 16) * RS);
-                const uint4* Tlo = reinterpret_cast<const uint4*>(T + (size_t)(lh & 0xffffu) * RS);
-                unsigned wp = 0u, s1p = 0u, s2p = 0u;
-                int c2 = 0, c3 = 0;
-#define TSFX_RANK_STEP(WN)                                                                     \
-                {                                                                              \
-                    const unsigned wn_ = (WN);                                                 \
-                    const unsigned s1n = __shfl_down_sync(FULL, wn_, 1), s2n = __shfl_down_sync(FULL, wn_, 2); \
-                    const unsigned m2 = wp & __funnelshift_r(s1p, s1n, 1);                     \
-                    const unsigned m3 = m2 & __funnelshift_r(s2p, s2n, 2);                     \
-                    c2 += __popc(m2);                                                          \
-                    c3 += __popc(m3);                                                          \
-                    wp = wn_; s1p = s1n; s2p = s2n;                                            \
-                }
-                for (int c = 0; c < (Wr >> 2); ++c) {
-                    const uint4 h = Thi[c], l = Tlo[c];
-                    TSFX_RANK_STEP(h.x & ~l.x)
-                    TSFX_RANK_STEP(h.y & ~l.y)
-                    TSFX_RANK_STEP(h.z & ~l.z)
-                    TSFX_RANK_STEP(h.w & ~l.w)
-                }
-                TSFX_RANK_STEP(0u)
+            };
+            if (Wr == 8) sweep(std::integral_constant<int, 2>());
+            else if (Wr == 4) sweep(std::integral_constant<int, 1>());
+            else if (Wr == 12) sweep(std::integral_constant<int, 3>());
+            else sweep(std::integral_constant<int, 0>());
 #undef TSFX_RANK_STEP
-                if (lane < 30 && i < n2) { l2 += lnk[c2]; iB += c2 - 1; }
-                if (lane < 30 && i < n3) { l3 += lnk[c3]; iA += c3 - 1; }
+            const double nl2 = (double)n2 * log((double)n2);      // sum_i log(c_i / N) = sum_i log(c_i) - N log(N)
+            const double nl3 = n3 > 0 ? (double)n3 * log((double)n3) : 0.0;
+            for (int q = 0; q < nq; ++q) {
+                double t2 = wsum(l2[q]), t3 = wsum(l3[q]);
+                double sB = (double)wsumi(iB[q]), sA = (double)wsumi(iA[q]);
+                if (G > 1) {
+                    if (lane == 0) { red[gw * 4 + 0] = t2; red[gw * 4 + 1] = t3; red[gw * 4 + 2] = sB; red[gw * 4 + 3] = sA; }
+                    __syncthreads();
+                    t2 = 0.0; t3 = 0.0; sB = 0.0; sA = 0.0;
+                    for (int w = 0; w < G; ++w) { t2 += red[w * 4 + 0]; t3 += red[w * 4 + 1]; sB += red[w * 4 + 2]; sA += red[w * 4 + 3]; }
+                    __syncthreads();
+                }
+                t2 -= nl2;
+                t3 -= nl3;
+                const Desc d = A.descs[dj + q];
+                double r;
+                if (d.calc == TSFX_SAMPLE_ENTROPY) r = -log(sA / sB);
+                else if (n <= 3) r = 0.0;                          // N <= m + 1
+                else r = fabs(t2 / (double)(n - 1) - t3 / (double)(n - 2));
+                if (tid == 0) orow[d.col] = r;
             }
-            l2 = wsum(l2); l3 = wsum(l3);
-            double sB = (double)wsumi(iB), sA = (double)wsumi(iA);
-            if (G > 1) {
-                if (lane == 0) { red[gw * 4 + 0] = l2; red[gw * 4 + 1] = l3; red[gw * 4 + 2] = sB; red[gw * 4 + 3] = sA; }
-                __syncthreads();
-                l2 = 0.0; l3 = 0.0; sB = 0.0; sA = 0.0;
-                for (int w = 0; w < G; ++w) { l2 += red[w * 4 + 0]; l3 += red[w * 4 + 1]; sB += red[w * 4 + 2]; sA += red[w * 4 + 3]; }
-            }
-            l2 -= (double)n2 * log((double)n2);               // sum_i log(c_i / N) = sum_i log(c_i) - N log(N)
-            l3 -= n3 > 0 ? (double)n3 * log((double)n3) : 0.0;
-            double r;
-            if (d.calc == TSFX_SAMPLE_ENTROPY) r = -log(sA / sB);
-            else if (n <= 3) r = 0.0;                          // N <= m + 1
-            else r = fabs(l2 / (double)(n - 1) - l3 / (double)(n - 2));
-            if (tid == 0) orow[d.col] = r;
-            gsync<G>();                                        // lohi / red are rewritten by the next tolerance
+            gsync<G>();                                            // the interval tables are rewritten by the next pair
         }
     }
 }
@@ -510,10 +558,15 @@ cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, 
         // rank-space kernel: warp per series while four working regions fit three CTAs per SM, then 4 / 16 warps per
         // series with the CTA sharing one prefix table; beyond that (n > ~1100) the pair-test tiles below take over
         const size_t lnk = (((size_t)A.npad + 1) * 8 + 15) & ~(size_t)15;
-        const size_t s1 = lnk + 4 * (size_t)rank_layout(A.npad, 1).bytes;
-        const size_t s4 = lnk + (size_t)rank_layout(A.npad, 4).bytes;
-        const size_t s16 = lnk + (size_t)rank_layout(A.npad, 16).bytes;
-        if (s1 <= 75 * 1024) return launch_rank<1, 4>(A, s1, 3, st, sm_count);
+        // TSFX_ENTROPY_PAD=1 pads the table rows to an odd multiple of 16 bytes (fewer bank conflicts, fewer resident warps)
+        static int pad = -1;
+        if (pad < 0) { const char* e = getenv("TSFX_ENTROPY_PAD"); pad = (e && e[0] == '1') ? 1 : 0; }
+        A.rank_pad = pad;
+        const size_t s1 = lnk + 4 * (size_t)rank_layout(A.npad, 1, pad).bytes;
+        const size_t s4 = lnk + (size_t)rank_layout(A.npad, 4, pad).bytes;
+        const size_t s16 = lnk + (size_t)rank_layout(A.npad, 16, pad).bytes;
+        const size_t sm_bytes = 227 * 1024;
+        if (s1 <= 75 * 1024) return launch_rank<1, 4>(A, s1, (int)std::min<size_t>(4, sm_bytes / (s1 + 1024)), st, sm_count);
         if (s4 <= 55 * 1024) return launch_rank<4, 1>(A, s4, 4, st, sm_count);
         if (s16 <= 226 * 1024) return launch_rank<16, 1>(A, s16, 1, st, sm_count);
     }

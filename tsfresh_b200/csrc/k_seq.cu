@@ -170,37 +170,30 @@ __device__ __forceinline__ unsigned pe_lehmer(unsigned bits, int D) {
 template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int n_sh[WPC];                     // length of the series each warp holds (the Lempel-Ziv lanes read it)
     __shared__ double clogc_small[64];            // c ln c for small counts (permutation histograms are mostly tiny)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) clogc_small[threadIdx.x] = threadIdx.x > 1 ? (double)threadIdx.x * log((double)threadIdx.x) : 0.0;
+    if (WPC * 32 < 64 && threadIdx.x < 32) clogc_small[32 + threadIdx.x] = (double)(32 + threadIdx.x) * log((double)(32 + threadIdx.x));
+    __syncthreads();
     unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
     unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
-    if (threadIdx.x < 64) clogc_small[threadIdx.x] = threadIdx.x > 1 ? (double)threadIdx.x * log((double)threadIdx.x) : 0.0;
-    __syncthreads();
 
-    // All warps of the CTA step through the series together (a warp past the end keeps a duplicate of the last
-    // series and stores nothing): the Lempel-Ziv parses of the CTA's WPC series are pooled -- lane t of the pooled
-    // warps runs (series t / cnt, bins parameter t % cnt) -- so the n sequential steps of a parse are issued once
-    // for up to 32 parses instead of once per series with 5 lanes busy.
-    for (int64_t s0 = (int64_t)blockIdx.x * WPC; s0 < A.R.n_series; s0 += warps_total) {
-        const bool live = (s0 + warp) < A.R.n_series;
-        const int64_t s = live ? (s0 + warp) : (A.R.n_series - 1);
+    for (int64_t s = (int64_t)blockIdx.x * WPC + warp; s < A.R.n_series; s += warps_total) {
         const int n = load_series(A.R, s, xs, lane);
         double* orow = A.out + (size_t)s * A.ncols;
         float lo = INFINITY, hi = -INFINITY;
         for (int i = lane; i < n; i += 32) { lo = fminf(lo, xs[i]); hi = fmaxf(hi, xs[i]); }
         const double vmin = (double)wminf(lo), vmax = (double)wmaxf(hi);
-        if (lane == 0) n_sh[warp] = n;
 
         int j = 0;
         while (j < A.nd) {
             const Desc d0 = A.descs[j];
             if (d0.calc == TSFX_LEMPEL_ZIV_COMPLEXITY) {
-                // up to lz_lanes consecutive LZ descriptors per batch
+                // up to lz_lanes consecutive LZ descriptors, one per lane
                 int cnt = 0;
                 while (j + cnt < A.nd && cnt < Y.lz_lanes && A.descs[j + cnt].calc == TSFX_LEMPEL_ZIV_COMPLEXITY) ++cnt;
                 for (int q = 0; q < cnt; ++q) {                      // symbols of every position, all lanes
@@ -209,40 +202,33 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                     unsigned short* sb = symbuf + (size_t)q * Y.npad;
                     for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
                 }
+                __syncwarp();
                 // phrase dictionary = prefix-closed trie stored as ONE open-addressing table of keys
                 // (parent slot << 16 | symbol); a node's id is the slot its key lives in, the root is 0xffff
                 {
                     unsigned* tab = reinterpret_cast<unsigned*>(trie);
                     for (int q = lane; q < cnt * Y.lz_hash; q += 32) tab[q] = 0xffffffffu;
                 }
-                __syncthreads();                                     // every warp's symbols and tables are in place
-                {
-                    const int t = warp * 32 + lane;                  // pooled task index
-                    if (t < WPC * cnt) {
-                        const int slot = t / cnt, q = t - slot * cnt;
-                        const bool slot_live = (s0 + slot) < A.R.n_series;
-                        const int64_t ss = slot_live ? (s0 + slot) : (A.R.n_series - 1);
-                        unsigned char* sbase = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, slot);
-                        const unsigned short* sb = reinterpret_cast<const unsigned short*>(sbase + Y.off_sym) + (size_t)q * Y.npad;
-                        unsigned* hkey = reinterpret_cast<unsigned*>(sbase + Y.off_trie) + (size_t)q * Y.lz_hash;
-                        const int ns = n_sh[slot];
-                        const Desc d = A.descs[j + q];
-                        const unsigned mask = (unsigned)Y.lz_hash - 1u;
-                        unsigned node = 0xffffu;
-                        int phrases = 0;
-                        for (int pos = 0; pos < ns; ++pos) {
-                            const unsigned key = (node << 16) | (unsigned)sb[pos];
-                            unsigned h = (key * 0x9E3779B1u) >> 15;
-                            h &= mask;
-                            unsigned k;
-                            while ((k = hkey[h]) != key && k != 0xffffffffu) h = (h + 1u) & mask;
-                            if (k == key) node = h;                      // phrase seen: extend it
-                            else { hkey[h] = key; ++phrases; node = 0xffffu; }
-                        }
-                        if (slot_live) A.out[(size_t)ss * A.ncols + d.col] = (double)phrases / (double)ns;
+                __syncwarp();
+                if (lane < cnt) {
+                    const Desc d = A.descs[j + lane];
+                    const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
+                    unsigned* hkey = reinterpret_cast<unsigned*>(trie) + (size_t)lane * Y.lz_hash;
+                    const unsigned mask = (unsigned)Y.lz_hash - 1u;
+                    unsigned node = 0xffffu;
+                    int phrases = 0;
+                    for (int pos = 0; pos < n; ++pos) {
+                        const unsigned key = (node << 16) | (unsigned)sb[pos];
+                        unsigned h = (key * 0x9E3779B1u) >> 15;
+                        h &= mask;
+                        unsigned k;
+                        while ((k = hkey[h]) != key && k != 0xffffffffu) h = (h + 1u) & mask;
+                        if (k == key) node = h;                      // phrase seen: extend it
+                        else { hkey[h] = key; ++phrases; node = 0xffffu; }
                     }
+                    orow[d.col] = (double)phrases / (double)n;
                 }
-                __syncthreads();                                     // tables are reused by the next batch / series
+                __syncwarp();
                 j += cnt;
             } else if (d0.calc == TSFX_PERMUTATION_ENTROPY) {
                 // run of permutation_entropy descriptors sharing tau: one pass over the windows serves all of
@@ -296,7 +282,7 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                             }
                             r = log((double)W) - wsum(acc) / (double)W;
                         }
-                        if (lane == 0 && live) orow[d.col] = r;
+                        if (lane == 0) orow[d.col] = r;
                         off += f;
                     }
                     __syncwarp();
@@ -326,11 +312,11 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                         r = log((double)W) - wsum(acc) / (double)W;
                         __syncwarp();
                     }
-                    if (lane == 0 && live) orow[d.col] = r;
+                    if (lane == 0) orow[d.col] = r;
                 }
                 j += cnt;
             } else {
-                if (lane == 0 && live) orow[d0.col] = dnan();
+                if (lane == 0) orow[d0.col] = dnan();
                 ++j;
             }
         }

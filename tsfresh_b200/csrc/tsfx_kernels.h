@@ -105,6 +105,8 @@ struct BasicArgs {
     double* out;
     int ncols;
     int npad, nscr, nlag, bytes_per_warp;   // shared-memory carve-up (doubles / doubles / doubles / bytes)
+    int lag_tiles;       // > 0: lag products by DMMA (mma.sync m8n8k4 f64) with this many 8 x 8 tiles; 0: FMA path
+    int desc_bytes;      // CTA-wide copy of the descriptor table in front of the per-warp regions (set by the launcher)
     int nxc, nalt;       // doubles of the centred copy incl. its zero tail; distinct agg_linear_trend (f_agg, chunk_len) keys
     int nfin;            // the first nfin descriptors are O(1) "finishers" (see k_basic.cu)
     int lag_needed;      // largest lag product any descriptor reads (0 = none)
@@ -174,6 +176,7 @@ struct LaArgs {
 cudaError_t launch_la(const LaArgs& A, int max_len, cudaStream_t st, int sm_count);
 
 struct EntropyArgs {
+    int rank_pad;              // rank-space kernel: pad the prefix-table rows (bank conflicts vs. occupancy)
     int xpad, bittile;         // padded sample count; 1 = bit-tile counting (default), 0 = pair sweep (TSFX_ENTROPY=pairs)
     SeriesRef R;
     unsigned char* gscratch;     // global scratch (API) -> set to nullptr by the launcher when shared memory is used

@@ -32,27 +32,11 @@ class B200Distributor(_reference_base()):
         self.device = device
 
     def map_reduce(self, map_function, data, function_kwargs=None, chunk_size=None, data_length=None):
-        from .extraction import _device_plan, get_context
+        from .extraction import do_extraction_on_chunks
         kw = function_kwargs or {}
-        default = kw.get("default_fc_parameters") or {}
-        per_kind = kw.get("kind_to_fc_parameters") or {}
-        ctx = get_context(self.device)
-        by_kind = {}
-        for sid, kind, series in data:              # the adapter already grouped by (id, kind) and sorted by time
-            by_kind.setdefault(str(kind), []).append((sid, np.asarray(series, dtype=np.float32)))
-        triples = []
-        for kind, items in by_kind.items():
-            plan = Plan(per_kind.get(kind, default))
-            if plan.n_cols == 0:
-                continue
-            dp = _device_plan(ctx, plan)
-            lens = np.array([len(v) for _, v in items], dtype=np.int32)
-            begin = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
-            mat = dp.extract_csr(np.concatenate([v for _, v in items]), begin, lens)
-            names = [kind + "__" + s for s in plan.suffixes]
-            for r, (sid, _) in enumerate(items):
-                triples.extend((sid, n, mat[r, c]) for c, n in enumerate(names))
-        return triples
+        # the adapter already grouped by (id, kind) and sorted by time; all chunks go to the device together
+        return do_extraction_on_chunks(data, kw.get("default_fc_parameters") or {}, kw.get("kind_to_fc_parameters") or {},
+                                       show_warnings=kw.get("show_warnings", False), device=self.device)
 
     def close(self):
         pass

@@ -170,6 +170,61 @@ def _encode_ids(id_series_list):
     return codes, uniq
 
 
+def do_extraction_on_chunks(chunks, default_fc_parameters, kind_to_fc_parameters=None, show_warnings=True, device=None):
+    """Batched form of the reference's per-series function (extraction.py:308-386): `chunks` is an iterable of
+    (sample_id, kind, data) with `data` a pandas.Series or 1-d array already ordered in time; every chunk of one kind
+    goes to the device in ONE launch set.  Returns the flat list of (sample_id, "kind__feature", value) triples in the
+    reference's order (chunk by chunk, settings order inside a chunk)."""
+    ctx = get_context(device)
+    by_kind, order = {}, []
+    for pos, (sid, kind, data) in enumerate(chunks):
+        idx = getattr(data, "index", None)
+        is_dt = isinstance(idx, pd.DatetimeIndex)
+        by_kind.setdefault((kind, is_dt), []).append((pos, sid, data))
+        order.append(None)
+    results = [None] * len(order)
+    for (kind, is_dt), items in by_kind.items():
+        if kind_to_fc_parameters and kind in kind_to_fc_parameters:
+            fc = kind_to_fc_parameters[kind]
+        else:
+            fc = default_fc_parameters
+        plan = Plan(fc, has_datetime_index=is_dt)
+        if show_warnings:
+            for name in plan.skipped:
+                warnings.warn("{} requires the data to have a index of type {}. Results will "
+                              "not be calculated".format(name, pd.DatetimeIndex))
+        names = [str(kind) + "__" + sfx for sfx in plan.suffixes]
+        if plan.n_cols == 0:
+            for pos, sid, _ in items:
+                results[pos] = []
+            continue
+        vals = [np.asarray(d, dtype=np.float32).reshape(-1) for _, _, d in items]
+        lens = np.array([len(v) for v in vals], dtype=np.int32)
+        if (lens < 1).any():
+            raise ValueError("empty time series in chunk")
+        begin = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        times = None
+        if plan.needs_times:
+            times = np.concatenate([d.index.as_unit("ns").asi8 for _, _, d in items])
+        try:
+            mat = _device_plan(ctx, plan).extract_csr(np.concatenate(vals), begin, lens, times=times)
+        except ValueError as e:
+            if "contains NaN" in str(e):
+                raise ValueError("Column must not contain NaN values: {}".format(kind)) from None
+            raise
+        for r, (pos, sid, _) in enumerate(items):
+            results[pos] = [(sid, n, mat[r, c]) for c, n in enumerate(names)]
+    return [t for chunk in results for t in chunk]
+
+
+def _do_extraction_on_chunk(chunk, default_fc_parameters, kind_to_fc_parameters, show_warnings=True):
+    """Drop-in for tsfresh.feature_extraction.extraction._do_extraction_on_chunk (extraction.py:308-386), the function
+    the dask / spark bindings call per (id, kind) group (convenience/bindings.py:50-54): same arguments, same list of
+    (sample_id, "kind__feature", value) triples -- evaluated by the GPU kernels.  One chunk per call wastes the device;
+    the bindings' map functions can collect groups and call do_extraction_on_chunks instead."""
+    return do_extraction_on_chunks([chunk], default_fc_parameters, kind_to_fc_parameters, show_warnings=show_warnings)
+
+
 def _extract_rolled(rolled, default_fc_parameters, kind_to_fc_parameters, impute_function, show_warnings, device):
     """extract_features(roll_time_series(...)): every window is a (begin, len) view on the kind's value buffer
     (tsfresh_b200.rolling); same result frame as the reference gives on its materialised rolled frame."""
