@@ -276,6 +276,22 @@ int64_t tsfx_roll_windows(const int64_t* begin, const int32_t* len, int64_t n_se
 int tsfx_impute(tsfx_ctx* ctx, double* matrix, int64_t n_rows, int32_t n_cols, int32_t mode, double* col_stats,
                 uint32_t flags);
 
+/* Feature selection on the feature matrix (tsfresh/feature_selection/relevance.py:31-322, significance_tests.py:43-132),
+ * classification targets: for every column of X ([n_rows x n_cols] row-major float64; host pointer, or device pointer with
+ * TSFX_FLAG_DEVICE_PTRS) and every class k (one-vs-rest, y_codes[i] in 0 .. n_classes-1, host) the sufficient statistics of
+ * the reference's univariate tests, from one sort of the column:
+ *   out[(k * n_cols + c) * TSFX_SEL_NSTAT + ...] =
+ *     0: feature type (0 constant, 1 binary, 2 real; get_feature_type relevance.py:325-345)   1: n1 = rows of class k   2: n0
+ *     real feature:    3: Mann-Whitney U of the class-k sample   4: tie term sum(t^3 - t)   5: two-sample KS statistic
+ *                      6: number of distinct values
+ *     binary feature:  3: n(y = k, x = larger value)  4: n(y = k, x = smaller)  5: n(y != k, x = larger)  6: n(y != k, x = smaller)
+ * (the contingency table of target_binary_feature_binary_test, significance_tests.py:70-79).  p-values and the
+ * Benjamini-Hochberg / -Yekutieli decision are O(n_cols) host work (tsfresh_b200/feature_selection.py).
+ * TSFX_E_NAN when X holds a NaN (the reference raises ValueError, significance_tests.py:266-289). */
+#define TSFX_SEL_NSTAT 8
+int tsfx_select_classification(tsfx_ctx* ctx, const double* X, int64_t n_rows, int32_t n_cols, const int32_t* y_codes,
+                               int32_t n_classes, double* out, uint32_t flags);
+
 /* Per-kernel-group device time (ms) of the last extract call made with TSFX_FLAG_TIMING.
  * names_out[i] points at a static string.  Returns the number of groups written (<= cap). */
 int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names_out, int32_t cap);

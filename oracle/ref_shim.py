@@ -49,7 +49,7 @@ def load():
     _stub("statsmodels.tools.sm_exceptions", MissingDataError=tp.MissingDataError)
     _stub("statsmodels.tsa.ar_model", AutoReg=tp.AutoReg)
     _stub("statsmodels.tsa.stattools", acf=tp.acf, adfuller=tp.adfuller, pacf=tp.pacf)
-    _stub("statsmodels.stats.multitest", multipletests=_missing)
+    _stub("statsmodels.stats.multitest", multipletests=tp.multipletests)
     sys.modules.setdefault("mock", unittest.mock)
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

@@ -228,3 +228,29 @@ def cwt(data, scales, wavelet="mexh", **_):
             raise ValueError("Selected scale of {} too small.".format(scale))
         out[i] = coef
     return out, None
+
+
+# ----------------------------------------------------------------------------- statsmodels.stats.multitest.multipletests
+def multipletests(pvals, alpha=0.05, method="fdr_bh", **_):
+    """multipletests(pvals, alpha, "fdr_bh" | "fdr_by") -> (reject, pvals_corrected, None, None): the Benjamini-Hochberg
+    step-up procedure (fdrcorrection, method "indep") and its Benjamini-Yekutieli variant ("negcorr": thresholds divided by
+    sum_{i<=m} 1/i).  Call site: tsfresh/feature_selection/relevance.py:347-351 (only element [0] is used)."""
+    if method not in ("fdr_bh", "fdr_by"):
+        raise NotImplementedError(method)
+    p = np.asarray(pvals, dtype=np.float64)
+    m = len(p)
+    order = np.argsort(p)
+    ps = p[order]
+    ecdf = np.arange(1, m + 1) / float(m)
+    if method == "fdr_by":
+        ecdf = ecdf / np.sum(1.0 / np.arange(1, m + 1))
+    reject = ps <= ecdf * alpha
+    if reject.any():
+        reject[:np.max(np.nonzero(reject)[0]) + 1] = True
+    corrected_raw = ps / ecdf
+    corrected = np.minimum.accumulate(corrected_raw[::-1])[::-1]
+    corrected[corrected > 1] = 1
+    out_r, out_c = np.empty(m, dtype=bool), np.empty(m)
+    out_r[order] = reject
+    out_c[order] = corrected
+    return out_r, out_c, None, None

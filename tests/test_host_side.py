@@ -280,3 +280,30 @@ def test_input_validation_matches_reference_wrong_input_cases():
         with pytest.raises(ValueError):
             to_tsdata(*case)
             pytest.fail("case %d did not raise" % k)
+
+
+def test_feature_selection_pvalues_match_scipy():
+    """host-side finishing of tsfresh_b200.feature_selection: the p-value of every statistic the device returns is the one
+    scipy computes from the raw samples (significance_tests.py:43-132)"""
+    from scipy import stats
+    from tsfresh_b200.feature_selection import benjamini_reject, fisher_pvalue, ks_2samp_pvalue, mannwhitneyu_pvalue
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        n1, n2 = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        if trial % 2:
+            x, y = rng.standard_normal(n1), rng.standard_normal(n2) + 0.4
+        else:
+            x, y = rng.integers(0, 6, n1).astype(float), rng.integers(0, 6, n2).astype(float)
+        ref = stats.mannwhitneyu(x, y, use_continuity=True, alternative="two-sided")
+        xy = np.concatenate([x, y])
+        U1 = stats.rankdata(xy)[:n1].sum() - n1 * (n1 + 1) / 2
+        _, t = np.unique(xy, return_counts=True)
+        p = mannwhitneyu_pvalue(U1, n1, n2, float((t ** 3 - t).sum()), len(t))
+        assert (np.isnan(p) and np.isnan(ref.pvalue)) or abs(p - ref.pvalue) < 1e-12
+        ks = stats.ks_2samp(x, y)
+        assert abs(ks_2samp_pvalue(ks.statistic, n1, n2) - ks.pvalue) < 1e-12
+    assert abs(fisher_pvalue(8, 2, 1, 5) - stats.fisher_exact([[8, 2], [1, 5]])[1]) < 1e-15
+    # Benjamini-Hochberg by hand: m = 4, alpha = 0.05 -> thresholds 0.0125, 0.025, 0.0375, 0.05
+    assert list(benjamini_reject([0.03, 0.001, 0.5, 0.02], 0.05, True)) == [True, True, False, True]
+    # Benjamini-Yekutieli divides the thresholds by 1 + 1/2 + 1/3 + 1/4
+    assert list(benjamini_reject([0.03, 0.001, 0.5, 0.02], 0.05, False)) == [False, True, False, False]

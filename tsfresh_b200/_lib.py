@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification"]
 
 
 def load():
@@ -71,6 +71,7 @@ def load():
         lib.tsfx_peer_flush.argtypes = [vp]
         lib.tsfx_set_max_len_hint.argtypes = [vp, i32]
         lib.tsfx_set_row_times.argtypes = [vp, vp, i64, u32]
+        lib.tsfx_select_classification.argtypes = [vp, vp, i64, i32, vp, i32, vp, u32]
         _lib = lib
         return lib
 
@@ -168,6 +169,17 @@ class Context:
         lib, h = self.lib, self.h
         weakref.finalize(buf, lambda lib=lib, h=h, p=p: lib.tsfx_host_free(h, ctypes.c_void_p(p)))
         return arr
+
+    def select_classification(self, X, y_codes, n_classes):
+        """tsfx_select_classification on a host matrix: returns [n_classes, n_cols, 8] sufficient statistics"""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y_codes, dtype=np.int32)
+        n, f = X.shape
+        out = np.zeros((int(n_classes), f, 8), dtype=np.float64)
+        with self.lock:
+            rc = self.lib.tsfx_select_classification(self.h, _ptr(X), n, f, _ptr(y), int(n_classes), _ptr(out), 0)
+            self.check(rc, "tsfx_select_classification")
+        return out
 
     def set_row_times(self, times_ns):
         """timestamps (int64 ns) of the rows of the NEXT extract call's values (linear_trend_timewise)"""

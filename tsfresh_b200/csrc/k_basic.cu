@@ -398,7 +398,7 @@ __device__ __noinline__ double basic_finisher(const Desc& d, const double* ST, c
 }
 
 template <int WPC, bool GS>
-__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_basic(BasicArgs A) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : (WPC == 12 ? 2 : 1))) k_basic(BasicArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the descriptor table is walked by every warp on every trip: one copy per CTA in shared memory (the global-memory
@@ -916,6 +916,31 @@ cudaError_t launch_basic(const BasicArgs& A0, int max_len, cudaStream_t st, int 
     A.gscratch = G.gscratch;
     G.smem += A.desc_bytes;                       // CTA-wide descriptor table in front of the per-warp regions
     if (G.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    {
+        // TSFX_BASIC_WPC=12|24: fewer, larger CTAs per SM (2 x 12 or 1 x 24 warps instead of 3 x 8): all warps of a CTA walk
+        // the descriptor list in lock step, so larger CTAs share more of the instruction stream (experiment knob)
+        static int wide = -1;
+        if (wide < 0) { const char* e = getenv("TSFX_BASIC_WPC"); wide = e ? atoi(e) : 0; }
+        if ((wide == 12 || wide == 24) && !G.gscratch && G.wpc == 8) {
+            const size_t smem = per * wide + A.desc_bytes;
+            if (smem <= 227 * 1024) {
+                const int64_t ctas = (A.R.n_series + wide - 1) / wide;
+                const int64_t cap = (int64_t)sm_count * grid_waves(4096);
+                const int grid = (int)std::max<int64_t>(1, std::min(ctas, cap));
+                cudaError_t e;
+                if (wide == 12) {
+                    e = cudaFuncSetAttribute(k_basic<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    k_basic<12, false><<<grid, 12 * 32, smem, st>>>(A);
+                } else {
+                    e = cudaFuncSetAttribute(k_basic<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    k_basic<24, false><<<grid, 24 * 32, smem, st>>>(A);
+                }
+                return cudaGetLastError();
+            }
+        }
+    }
     TSFX_DISPATCH(k_basic, G, st, A)
     return cudaGetLastError();
 }

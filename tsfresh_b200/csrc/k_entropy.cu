@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
     const int grp = threadIdx.x / NTHR;                 // series slot inside the CTA
     const int tid = threadIdx.x - grp * NTHR;           // thread inside the series group
     const int gw = tid >> 5;                            // warp inside the series group
-    const RankLayout L = rank_layout(A.npad, G, A.rank_pad);
+    const RankLayout L = rank_layout(A.npad, G, G > 1 ? 1 : A.rank_pad);
     double* lnk = reinterpret_cast<double*>(smem_raw);                              // log(k), k = 0..npad (CTA-wide)
     unsigned char* base = smem_raw + (((A.npad + 1) * 8 + 15) & ~15) + (size_t)grp * L.bytes;
     unsigned* T = reinterpret_cast<unsigned*>(base + L.t_off);
@@ -379,72 +379,103 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
             // step with the exact predicate, then ONE binary search over the sorted keys.  hi needs no second search:
             // the relation is symmetric (a <= hi(r) <=> lo(a) <= r), so hi(r) + 1 = #{ a : lo(a) <= r } = the inclusive
             // prefix sum of the histogram of lo.
-            for (int q = 0; q < nq; ++q) {
-                unsigned* lh = lohi + (size_t)q * L.lh_stride;
-                const double tau = tauq[q];
-                const bool sane = tau >= 0.0;                    // NaN / negative tolerance: every comparison is false
-                for (int r = tid; r <= n; r += NTHR) cnt[r] = 0u;
-                gsync<G>();
-                if (sane) {
-                    constexpr int U = 4;                                 // ranks per lane in flight (independent chains)
-                    for (int r0 = tid; r0 < n; r0 += U * NTHR) {
-                        unsigned kL[U];
-                        int pos[U];
+            // both tolerances of the pair are searched together (2 x U independent chains per lane); their histograms
+            // share one array (tolerance 0 in the low, tolerance 1 in the high 16 bits of each counter: counts are <= n)
+            const bool sane0 = tauq[0] >= 0.0, sane1 = nq > 1 && tauq[1] >= 0.0;      // NaN / negative: every comparison is false
+            unsigned* lhq[2] = {lohi, lohi + L.lh_stride};
+            for (int r = tid; r <= n; r += NTHR) cnt[r] = 0u;
+            gsync<G>();
+            {
+                constexpr int U = 4;                                 // ranks per lane and tolerance in flight
+                for (int r0 = tid; r0 < n; r0 += U * NTHR) {
+                    unsigned kL[2][U];
+                    int pos[2][U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int r = r0 + u * NTHR;
-                            const double sr = (double)key_f32(sk[r < n ? r : 0]);
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * NTHR;
+                        const double sr = (double)key_f32(sk[r < n ? r : 0]);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const double tau = tauq[q];
                             float Lf = __double2float_ru(sr - tau);
                             if (!((sr - (double)Lf) <= tau)) Lf = key_f32(f32_key(Lf) + 1u);       // one float32 step up
                             else {
                                 const float Lp = key_f32(f32_key(Lf) - 1u);                          // one step down still inside?
                                 if ((sr - (double)Lp) <= tau) Lf = Lp;
                             }
-                            kL[u] = f32_key(Lf);
-                            pos[u] = 0;
+                            kL[q][u] = f32_key(Lf);
+                            pos[q][u] = 0;
                         }
-                        for (int st = N2 >> 1; st > 0; st >>= 1) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u)
-                                if (sk[pos[u] + st - 1] < kL[u]) pos[u] += st;
-                        }
+                    }
+                    for (int st = N2 >> 1; st > 0; st >>= 1) {
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const int r = r0 + u * NTHR;
-                            if (r < n) {
-                                // (N2 a power of two >= n: the search above covers [0, N2 - 1]; a count of N2 - 1 can only
-                                // be short by the last element, checked here)
-                                int lo = pos[u];
-                                if (lo == N2 - 1 && sk[N2 - 1] < kL[u]) lo = N2;
-                                lh[r] = (unsigned)lo;
-                                atomicAdd(&cnt[lo], 1u);
-                            }
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+                                if (sk[pos[q][u] + st - 1] < kL[q][u]) pos[q][u] += st;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = r0 + u * NTHR;
+                        if (r < n) {
+                            // (N2 a power of two >= n: the search above covers [0, N2 - 1]; a count of N2 - 1 can only
+                            // be short by the last element, checked here)
+                            int lo0 = pos[0][u], lo1 = pos[1][u];
+                            if (lo0 == N2 - 1 && sk[N2 - 1] < kL[0][u]) lo0 = N2;
+                            if (lo1 == N2 - 1 && sk[N2 - 1] < kL[1][u]) lo1 = N2;
+                            if (sane0) { lhq[0][r] = (unsigned)lo0; atomicAdd(&cnt[lo0], 1u); }
+                            if (sane1) { lhq[1][r] = (unsigned)lo1; atomicAdd(&cnt[lo1], 0x10000u); }
                         }
                     }
                 }
-                gsync<G>();
-                if (gw == 0) {          // inclusive scan of the histogram by one warp: lane l owns a contiguous run of ranks
-                    const int run = (n + 31) >> 5;
-                    const int b0 = lane * run;
+            }
+            gsync<G>();
+            if (gw == 0) {              // inclusive scan of the histograms by one warp: lane l owns a contiguous run of ranks
+                const int run = (n + 31) >> 5;
+                const int b0 = lane * run;
+                if (run <= 8) {         // the run lives in registers: one dependent shared-memory round trip, not one per rank
+                    unsigned v[8];
+                    unsigned tot = 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const int r = b0 + k; v[k] = (k < run && r < n) ? cnt[r] : 0u; }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { tot += v[k]; v[k] = tot; }
+                    unsigned inc = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned w = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += w; }
+                    const unsigned off = inc - tot;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = b0 + k;
+                        if (k < run && r < n) {
+                            const unsigned acc = off + v[k];
+                            lhq[0][r] = sane0 ? (lhq[0][r] | (acc << 16)) : 0x00010001u;       // lo | (hi + 1) << 16; empty: T[1] & ~T[1]
+                            if (nq > 1) lhq[1][r] = sane1 ? (lhq[1][r] | (acc & 0xffff0000u)) : 0x00010001u;
+                        }
+                    }
+                } else {
                     unsigned tot = 0u;
                     for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
                     unsigned inc = tot;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned w = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += w; }
                     unsigned acc = inc - tot;
                     for (int k = 0; k < run; ++k) {
                         const int r = b0 + k;
                         if (r < n) {
                             acc += cnt[r];
-                            lh[r] = sane ? (lh[r] | (acc << 16)) : 0x00010001u;       // lo | (hi + 1) << 16; empty: T[1] & ~T[1]
+                            lhq[0][r] = sane0 ? (lhq[0][r] | (acc << 16)) : 0x00010001u;
+                            if (nq > 1) lhq[1][r] = sane1 ? (lhq[1][r] | (acc & 0xffff0000u)) : 0x00010001u;
                         }
                     }
                 }
-                gsync<G>();
             }
+            gsync<G>();
             // ---- phase B: template counts, lane = row (30 rows per block: rows i+1, i+2 come from the next lanes)
             double l2[2] = {0.0, 0.0}, l3[2] = {0.0, 0.0};
             int iB[2] = {0, 0}, iA[2] = {0, 0};
+            const double ln_n2 = n2 > 0 ? lnk[n2] : 0.0, ln_n3 = n3 > 0 ? lnk[n3] : 0.0;
             const unsigned* lh1 = lohi + (nq > 1 ? L.lh_stride : 0);
 #define TSFX_RANK_STEP(Q, WN)                                                                  \
             {                                                                                  \
@@ -492,9 +523,9 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
                     }
                     TSFX_RANK_STEP(0, 0u) TSFX_RANK_STEP(1, 0u)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (lane < 30 && i < n2) { l2[q] += lnk[c2[q]]; iB[q] += c2[q] - 1; }
-                        if (lane < 30 && i < n3) { l3[q] += lnk[c3[q]]; iA[q] += c3[q] - 1; }
+                    for (int q = 0; q < 2; ++q) {      // log(c / N) as log c - log N per row: exactly 0 when every template matches
+                        if (lane < 30 && i < n2) { l2[q] += lnk[c2[q]] - ln_n2; iB[q] += c2[q] - 1; }
+                        if (lane < 30 && i < n3) { l3[q] += lnk[c3[q]] - ln_n3; iA[q] += c3[q] - 1; }
                     }
                 }
             };
@@ -503,8 +534,6 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
             else if (Wr == 12) sweep(std::integral_constant<int, 3>());
             else sweep(std::integral_constant<int, 0>());
 #undef TSFX_RANK_STEP
-            const double nl2 = (double)n2 * log((double)n2);      // sum_i log(c_i / N) = sum_i log(c_i) - N log(N)
-            const double nl3 = n3 > 0 ? (double)n3 * log((double)n3) : 0.0;
             for (int q = 0; q < nq; ++q) {
                 double t2 = wsum(l2[q]), t3 = wsum(l3[q]);
                 double sB = (double)wsumi(iB[q]), sA = (double)wsumi(iA[q]);
@@ -515,8 +544,6 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
                     for (int w = 0; w < G; ++w) { t2 += red[w * 4 + 0]; t3 += red[w * 4 + 1]; sB += red[w * 4 + 2]; sA += red[w * 4 + 3]; }
                     __syncthreads();
                 }
-                t2 -= nl2;
-                t3 -= nl3;
                 const Desc d = A.descs[dj + q];
                 double r;
                 if (d.calc == TSFX_SAMPLE_ENTROPY) r = -log(sA / sB);
@@ -563,8 +590,9 @@ cudaError_t launch_entropy(const EntropyArgs& A0, int max_len, cudaStream_t st, 
         if (pad < 0) { const char* e = getenv("TSFX_ENTROPY_PAD"); pad = (e && e[0] == '1') ? 1 : 0; }
         A.rank_pad = pad;
         const size_t s1 = lnk + 4 * (size_t)rank_layout(A.npad, 1, pad).bytes;
-        const size_t s4 = lnk + (size_t)rank_layout(A.npad, 4, pad).bytes;
-        const size_t s16 = lnk + (size_t)rank_layout(A.npad, 16, pad).bytes;
+        // several warps per series: rows are always padded (an unpadded 128-byte row stride puts every row on the same banks)
+        const size_t s4 = lnk + (size_t)rank_layout(A.npad, 4, 1).bytes;
+        const size_t s16 = lnk + (size_t)rank_layout(A.npad, 16, 1).bytes;
         const size_t sm_bytes = 227 * 1024;
         if (s1 <= 75 * 1024) return launch_rank<1, 4>(A, s1, (int)std::min<size_t>(4, sm_bytes / (s1 + 1024)), st, sm_count);
         if (s4 <= 55 * 1024) return launch_rank<4, 1>(A, s4, 4, st, sm_count);

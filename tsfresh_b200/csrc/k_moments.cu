@@ -49,13 +49,45 @@ __device__ __forceinline__ float gmaxf(float v) {
     return v;
 }
 
-struct MomStats { double n, sum, sumsq, mean, m2, m3, m4, var, sd, vmin, vmax, x0, xn1; };
+struct MomStats { double n, sum, sumsq, mean, m2, m3, m4, var, sd, vmin, vmax, x0, xn1, rms, absmax, skew, kurt; };
 
-__device__ __noinline__ double moments_value(const Desc& d, const MomStats& S) {
+// the square roots / divisions every column shares are formed ONCE per series by all lanes (uniform code); the
+// per-descriptor pick below is then a couple of instructions per lane instead of a divergent walk through ten cases
+__device__ __forceinline__ void moments_derive(MomStats& S, int need_high) {
     const double dn = S.n;
-    const int n = (int)dn;
+    S.var = S.m2 / dn;
+    S.sd = sqrt(S.var);
+    S.rms = sqrt(S.sumsq / dn);
+    S.absmax = fmax(fabs(S.vmin), fabs(S.vmax));
+    S.skew = dnan();
+    S.kurt = dnan();
+    if (need_high) {
+        const int n = (int)dn;
+        const double e1 = 2.220446049250313e-16 * S.absmax, e2 = e1 * e1;
+        {   // pandas nanops.nanskew
+            double m2 = S.m2, m3 = S.m3;
+            if (fabs(m2) < e2 * dn) m2 = 0.0;
+            if (fabs(m3) < e2 * e1 * dn) m3 = 0.0;
+            if (n >= 3) S.skew = (m2 == 0.0) ? 0.0 : (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2)));
+        }
+        {   // pandas nanops.nankurt
+            double m2 = S.m2, m4 = S.m4;
+            if (fabs(m2) < e2 * dn) m2 = 0.0;
+            if (fabs(m4) < e2 * e2 * dn) m4 = 0.0;
+            if (n >= 4) {
+                const double adj = 3.0 * (dn - 1.0) * (dn - 1.0) / ((dn - 2.0) * (dn - 3.0));
+                const double num = dn * (dn + 1.0) * (dn - 1.0) * m4;
+                const double den = (dn - 2.0) * (dn - 3.0) * m2 * m2;
+                S.kurt = (den == 0.0) ? 0.0 : num / den - adj;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double moments_value(const Desc& d, const MomStats& S) {
+    const double dn = S.n;
     switch (d.calc) {
-        case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: return (S.var > sqrt(S.var)) ? 1.0 : 0.0;
+        case TSFX_VARIANCE_LARGER_THAN_STANDARD_DEVIATION: return (S.var > S.sd) ? 1.0 : 0.0;      // sd = sqrt(var)
         case TSFX_LARGE_STANDARD_DEVIATION: return (S.sd > d.p0 * (S.vmax - S.vmin)) ? 1.0 : 0.0;
         case TSFX_SUM_VALUES: return S.sum;
         case TSFX_ABS_ENERGY: return S.sumsq;
@@ -64,33 +96,13 @@ __device__ __noinline__ double moments_value(const Desc& d, const MomStats& S) {
         case TSFX_STANDARD_DEVIATION: return S.sd;
         case TSFX_VARIANCE: return S.var;
         case TSFX_VARIATION_COEFFICIENT: return (S.mean != 0.0) ? S.sd / S.mean : dnan();
-        case TSFX_ROOT_MEAN_SQUARE: return sqrt(S.sumsq / dn);
+        case TSFX_ROOT_MEAN_SQUARE: return S.rms;
         case TSFX_MAXIMUM: return S.vmax;
         case TSFX_MINIMUM: return S.vmin;
-        case TSFX_ABSOLUTE_MAXIMUM: return fmax(fabs(S.vmin), fabs(S.vmax));
-        case TSFX_MEAN_CHANGE: return n > 1 ? (S.xn1 - S.x0) / (double)(n - 1) : dnan();
-        case TSFX_SKEWNESS: {   // pandas nanops.nanskew
-            const double amax = fmax(fabs(S.vmin), fabs(S.vmax));
-            const double e1 = 2.220446049250313e-16 * amax;
-            double m2 = S.m2, m3 = S.m3;
-            if (fabs(m2) < e1 * e1 * dn) m2 = 0.0;
-            if (fabs(m3) < e1 * e1 * e1 * dn) m3 = 0.0;
-            if (n < 3) return dnan();
-            if (m2 == 0.0) return 0.0;
-            return (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2)));
-        }
-        case TSFX_KURTOSIS: {   // pandas nanops.nankurt
-            const double amax = fmax(fabs(S.vmin), fabs(S.vmax));
-            const double e1 = 2.220446049250313e-16 * amax, e2 = e1 * e1;
-            double m2 = S.m2, m4 = S.m4;
-            if (fabs(m2) < e2 * dn) m2 = 0.0;
-            if (fabs(m4) < e2 * e2 * dn) m4 = 0.0;
-            if (n < 4) return dnan();
-            const double adj = 3.0 * (dn - 1.0) * (dn - 1.0) / ((dn - 2.0) * (dn - 3.0));
-            const double num = dn * (dn + 1.0) * (dn - 1.0) * m4;
-            const double den = (dn - 2.0) * (dn - 3.0) * m2 * m2;
-            return (den == 0.0) ? 0.0 : num / den - adj;
-        }
+        case TSFX_ABSOLUTE_MAXIMUM: return S.absmax;
+        case TSFX_MEAN_CHANGE: return dn > 1.0 ? (S.xn1 - S.x0) / (dn - 1.0) : dnan();
+        case TSFX_SKEWNESS: return S.skew;
+        case TSFX_KURTOSIS: return S.kurt;
         default: return dnan();       // query_similarity_count (default query=None), constant-NaN columns
     }
 }
@@ -196,10 +208,9 @@ __global__ void __launch_bounds__(WPC * 32, 3) k_moments(MomentsArgs A) {
         S.m2 = gsum<SUB>(a2);
         S.m3 = A.need_high ? gsum<SUB>(a3) : 0.0;
         S.m4 = A.need_high ? gsum<SUB>(a4) : 0.0;
-        S.var = S.m2 / S.n;
-        S.sd = sqrt(S.var);
         S.x0 = (live && n > 0) ? (double)__ldg(src) : 0.0;
         S.xn1 = (live && n > 0) ? (double)__ldg(src + n - 1) : 0.0;
+        moments_derive(S, A.need_high);
         if (live) {
             double* orow = A.out + (size_t)s * A.ncols;
             for (int j = sub; j < A.nd; j += SUB) {
@@ -271,8 +282,6 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_moments_dense(MomentsArgs A) {
         S.m2 = gsum<SUB>(a2);
         S.m3 = A.need_high ? gsum<SUB>(a3) : 0.0;
         S.m4 = A.need_high ? gsum<SUB>(a4) : 0.0;
-        S.var = S.m2 / S.n;
-        S.sd = sqrt(S.var);
         // first / last sample: lane `sub == 0` holds x[0] in its first chunk; x[n-1] sits in chunk n4 - 1
         const int lastc = n4 - 1, lk = lastc / SUB, lsub = lastc % SUB;
         float xl = 0.f;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_moments_dense(MomentsArgs A) {
         for (int k = 0; k < REG; ++k) if (k == lk) xl = cur[k].w;
         S.x0 = (double)__shfl_sync(FULL, cur[0].x, slot * SUB);
         S.xn1 = (double)__shfl_sync(FULL, xl, slot * SUB + lsub);
+        moments_derive(S, A.need_high);
         if (live) {
             double* orow = A.out + (size_t)s * A.ncols;
             for (int j = sub; j < A.nd; j += SUB) {

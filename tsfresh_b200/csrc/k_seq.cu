@@ -18,6 +18,8 @@ namespace tsfx {
 #define LZ_LANES 8
 
 struct SeqLayout {
+    int hot_bytes, hot_lines, hot_map, hot_bits;     // k_peaks from the global working region: the small, latency-critical
+                                                     // tables (ridge lines, column map, maxima bits) stay in shared memory
     int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride, nxd;
     int off_rowsf, off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs, off_xd;   // byte offsets
 };
@@ -334,9 +336,12 @@ __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
     double* noise = reinterpret_cast<double*>(base + Y.off_noise);         // npad : memoised noise floor (NaN = not yet)
     float* rowsf = reinterpret_cast<float*>(base + Y.off_rowsf);           // (cwt_n - 1) x npad : wider rows, float32 copies
     double* hw = reinterpret_cast<double*>(base + Y.off_hw);
-    unsigned* maxbits = reinterpret_cast<unsigned*>(base + Y.off_bits);
-    short* lines = reinterpret_cast<short*>(base + Y.off_lines);
-    int* colmap = reinterpret_cast<int*>(base + Y.off_map);
+    // ridge-line bookkeeping is a chain of dependent small-table lookups: from the global region every one of them is
+    // an L2 round trip (the hottest stalls of the kernel), so these tables get their own shared-memory slice
+    unsigned char* hot = (GS && Y.hot_bytes > 0) ? smem_raw + (size_t)warp * Y.hot_bytes : nullptr;
+    unsigned* maxbits = hot ? reinterpret_cast<unsigned*>(hot + Y.hot_bits) : reinterpret_cast<unsigned*>(base + Y.off_bits);
+    short* lines = hot ? reinterpret_cast<short*>(hot + Y.hot_lines) : reinterpret_cast<short*>(base + Y.off_lines);
+    int* colmap = hot ? reinterpret_cast<int*>(hot + Y.hot_map) : reinterpret_cast<int*>(base + Y.off_map);
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     double* xd = reinterpret_cast<double*>(base + Y.off_xd);               // zero-padded float64 copy for the convolutions
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
@@ -570,6 +575,20 @@ cudaError_t launch_peaks(const SeqArgs& A0, int max_len, cudaStream_t st, int sm
     Geometry G;
     if (!plan_geometry(per, 72 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G, 16 * 1024)) return cudaErrorInvalidConfiguration;
     A.gscratch = G.gscratch;
+    if (G.gscratch) {
+        // hybrid placement: bulk rows in the global (L2-resident) region, hot tables in shared memory when four CTAs
+        // per SM still fit
+        const size_t lines_b = (size_t)(A.npad + A.npad / 2 + 32) * (5 * 2 + 3 * 4);
+        const size_t map_b = (size_t)A.npad * 4, bits_b = (size_t)Y.cwt_n * Y.nwords * 4;
+        size_t hot = ((lines_b + 15) & ~(size_t)15) + ((map_b + 15) & ~(size_t)15) + ((bits_b + 15) & ~(size_t)15);
+        if (hot * G.wpc <= 54 * 1024) {
+            Y.hot_lines = 0;
+            Y.hot_map = (int)((lines_b + 15) & ~(size_t)15);
+            Y.hot_bits = Y.hot_map + (int)((map_b + 15) & ~(size_t)15);
+            Y.hot_bytes = (int)hot;
+            G.smem = hot * G.wpc;
+        }
+    }
     TSFX_DISPATCH(k_peaks, G, st, A, Y)
     return cudaGetLastError();
 }

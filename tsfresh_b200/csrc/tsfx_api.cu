@@ -18,6 +18,7 @@
 #include "tsfx_kernels.h"
 #include "tsfx_csr.h"
 #include "tsfx_impute.h"
+#include "tsfx_select.h"
 
 using namespace tsfx;
 
@@ -235,6 +236,8 @@ struct tsfx_ctx {
     int launches = 0;
     CsrWorkspace csr;
     ImputeWorkspace imp;
+    SelectWorkspace sel;
+    DevBuf sel_x, sel_y, sel_out;
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     int held_max_len = 0;
     bool used_moments = false;   // the last pass ran k_moments in place of k_basic (reported as "moments")
@@ -386,6 +389,8 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     ctx->times.release(); ctx->times_sorted.release();
     ctx->csr.release();
     ctx->imp.release();
+    ctx->sel.release();
+    ctx->sel_x.release(); ctx->sel_y.release(); ctx->sel_out.release();
     ctx->stager.release();
     ctx->pool.release_all();
     if (ctx->s_peer) cudaStreamDestroy(ctx->s_peer);
@@ -1258,6 +1263,40 @@ extern "C" void* tsfx_host_alloc(tsfx_ctx* ctx, size_t bytes) {
 }
 extern "C" void tsfx_host_free(tsfx_ctx* ctx, void* p) {
     if (ctx && p) ctx->pool.free(p);
+}
+
+// ------------------------------------------------------------------------------------------ feature selection
+extern "C" int tsfx_select_classification(tsfx_ctx* ctx, const double* X, int64_t n_rows, int32_t n_cols, const int32_t* y_codes,
+                                          int32_t n_classes, double* out, uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (n_rows < 1 || n_cols < 0 || n_classes < 1 || !y_codes || !out || (n_cols > 0 && !X))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_select_classification: bad arguments");
+    if (n_cols == 0) return TSFX_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int64_t> counts(n_classes, 0);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if (y_codes[i] < 0 || y_codes[i] >= n_classes) return fail(ctx, TSFX_E_INVALID, "class code out of range");
+        counts[y_codes[i]] += 1;
+    }
+    const double* d_X = X;
+    if (!(flags & TSFX_FLAG_DEVICE_PTRS)) {
+        CK(ctx->sel_x.reserve((size_t)n_rows * n_cols * 8));
+        CK(ctx->stager.h2d(ctx->sel_x.p, X, (size_t)n_rows * n_cols * 8, ctx->stream));
+        d_X = (const double*)ctx->sel_x.p;
+    }
+    CK(ctx->sel_y.reserve((size_t)n_rows * 4));
+    CK(ctx->stager.h2d(ctx->sel_y.p, y_codes, (size_t)n_rows * 4, ctx->stream));
+    const size_t ob = (size_t)n_classes * n_cols * TSFX_SEL_NSTAT * sizeof(double);
+    CK(ctx->sel_out.reserve(ob));
+    std::string msg;
+    int has_nan = 0;
+    int rc = select_class_stats(ctx->sel, d_X, n_rows, n_cols, (const int32_t*)ctx->sel_y.p, n_classes, counts.data(),
+                                (double*)ctx->sel_out.p, &has_nan, ctx->stream, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    CK(cudaMemcpyAsync(out, ctx->sel_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (has_nan) return fail(ctx, TSFX_E_NAN, "the feature matrix contains NaN");
+    return TSFX_OK;
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU placement
