@@ -225,6 +225,15 @@ int tsfx_extract_long_alloc(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t*
                             int32_t sort_key_is_f64, const float* values, int64_t n_rows, int64_t** out_ids,
                             double** out, int64_t* n_series_out, uint32_t flags);
 
+/* Wide format with a KIND dimension (data.py:181-230 WideTsFrameAdapter: several value columns share the id and sort
+ * columns): stage (a) runs once, every kind k is then evaluated with its own plan (kind_to_fc_parameters, extraction.py:
+ * 333-336) on its own value column values[k], and the result is ONE matrix [n_series x sum_k n_cols(k)] whose column
+ * blocks follow the order of the kinds -- the frame PartitionedTsData.pivot builds (data.py:86-121).  Result buffers come
+ * from the pinned pool (tsfx_host_free).  Up to 64 kinds per call. */
+int tsfx_extract_long_kinds(tsfx_ctx* ctx, const tsfx_plan* const* plans, const int64_t* ids, const void* sort_keys,
+                            int32_t sort_key_is_f64, const float* const* values, int32_t n_kinds, int64_t n_rows,
+                            int64_t** out_ids, double** out, int64_t* n_series_out, uint32_t flags);
+
 /* Page-locked host memory from the context's pool (freed blocks are cached: page-locking is slow). */
 void* tsfx_host_alloc(tsfx_ctx* ctx, size_t bytes);
 void tsfx_host_free(tsfx_ctx* ctx, void* p);

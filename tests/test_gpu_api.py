@@ -257,3 +257,35 @@ def test_do_extraction_on_chunk_signature():
     assert [t[:2] for t in out[:plan.n_cols]] == [(1, "a__" + c) for c in plan.suffixes]
     assert out[plan.n_cols:plan.n_cols + 2] == [(1, "b__maximum", float(y.max())), (1, "b__minimum", float(y.min()))]
     assert len(out) == 2 * plan.n_cols + 2
+
+
+def test_wide_format_kind_dimension_on_the_device():
+    """several value columns of one frame: ONE stage (a), per-kind settings, one result matrix (tsfx_extract_long_kinds);
+    rows in order, shuffled, and with keys shuffled inside the ids -- same frame as the per-kind path"""
+    rng = np.random.default_rng(31)
+    lens = rng.integers(5, 60, 300)
+    ids = np.repeat(np.arange(300) * 2 + 1, lens)
+    t = np.concatenate([np.arange(l) for l in lens])
+    df = pd.DataFrame({"id": ids, "time": t, "a": rng.standard_normal(len(ids)).astype(np.float32),
+                       "b": rng.standard_normal(len(ids)).astype(np.float32).cumsum(), 7: rng.random(len(ids)).astype(np.float32)})
+    s = EfficientFCParameters()
+    per_kind = {"b": MinimalFCParameters(), 7: {"maximum": None, "quantile": [{"q": 0.25}]}}
+    X = extract_features(df, column_id="id", column_sort="time", default_fc_parameters=s, kind_to_fc_parameters=per_kind)
+    plan_a = Plan(s)
+    assert list(X.columns) == ["a__" + c for c in plan_a.suffixes] + ["b__" + c for c in Plan(MinimalFCParameters()).suffixes] + \
+        ["7__maximum", "7__quantile__q_0.25"]
+    assert list(X.index) == sorted(set(ids))
+    series_a = [df["a"].to_numpy()[ids == i] for i in X.index]
+    assert not compare(X.to_numpy()[:, :plan_a.n_cols], oracle_rows([v.astype(np.float64) for v in series_a], s), plan_a.suffixes)
+    np.testing.assert_allclose(X["7__maximum"].to_numpy(), [df[7].to_numpy()[ids == i].max() for i in X.index])
+    # single-kind calls give the same blocks
+    Xb = extract_features(df[["id", "time", "b"]], column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters())
+    assert np.array_equal(X[[c for c in X.columns if c.startswith("b__")]].to_numpy(), Xb.to_numpy(), equal_nan=True)
+    for frame in (df.sample(frac=1.0, random_state=1), df.iloc[np.lexsort((rng.random(len(df)), ids))]):
+        Y = extract_features(frame, column_id="id", column_sort="time", default_fc_parameters=s, kind_to_fc_parameters=per_kind)
+        assert list(Y.columns) == list(X.columns) and np.array_equal(Y.to_numpy(), X.to_numpy(), equal_nan=True)
+    # a NaN in any kind is the reference's ValueError
+    bad = df.copy()
+    bad.loc[17, "b"] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        extract_features(bad, column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters())

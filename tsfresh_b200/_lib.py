@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification", "tsfx_extract_long_kinds"]
 
 
 def load():
@@ -72,6 +72,8 @@ def load():
         lib.tsfx_set_max_len_hint.argtypes = [vp, i32]
         lib.tsfx_set_row_times.argtypes = [vp, vp, i64, u32]
         lib.tsfx_select_classification.argtypes = [vp, vp, i64, i32, vp, i32, vp, u32]
+        lib.tsfx_extract_long_kinds.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                ctypes.POINTER(i64), u32]
         _lib = lib
         return lib
 
@@ -283,6 +285,38 @@ class DevicePlan:
                                            ctypes.c_void_p(begin_ptr), ctypes.c_void_p(len_ptr), n_series,
                                            ctypes.c_void_p(out_ptr), flags)
         self.ctx.check(rc, "tsfx_extract_csr")
+
+
+def extract_long_kinds(ctx, device_plans, ids, sort_keys, value_columns, flags=0, times=None):
+    """Wide format: K value columns sharing ids / sort keys, one DevicePlan per kind -> (unique ids, matrix
+    [n_ids x sum of the plans' columns]) from ONE stage (a) (tsfx_extract_long_kinds)."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    cols = [np.ascontiguousarray(v, dtype=np.float32) for v in value_columns]
+    assert len(cols) == len(device_plans) and all(len(c) == len(ids) for c in cols)
+    is_f64 = 0
+    if sort_keys is not None:
+        sort_keys = np.asarray(sort_keys)
+        if sort_keys.dtype.kind == "f":
+            sort_keys = np.ascontiguousarray(sort_keys, dtype=np.float64)
+            is_f64 = 1
+        else:
+            sort_keys = np.ascontiguousarray(sort_keys, dtype=np.int64)
+    K = len(cols)
+    plan_arr = (ctypes.c_void_p * K)(*[dp.h for dp in device_plans])
+    val_arr = (ctypes.c_void_p * K)(*[c.ctypes.data for c in cols])
+    total = sum(dp.n_cols for dp in device_plans)
+    n_series = ctypes.c_int64(0)
+    p_ids, p_out = ctypes.c_void_p(), ctypes.c_void_p()
+    with ctx.lock:
+        if times is not None:
+            ctx.set_row_times(times)
+        rc = ctx.lib.tsfx_extract_long_kinds(ctx.h, plan_arr, _ptr(ids), _ptr(sort_keys), is_f64, val_arr, K, len(ids),
+                                             ctypes.byref(p_ids), ctypes.byref(p_out), ctypes.byref(n_series), flags)
+        ctx.check(rc, "tsfx_extract_long_kinds")
+    k = n_series.value
+    if k == 0 or not p_out.value:
+        return np.empty(0, dtype=np.int64), np.empty((0, total), dtype=np.float64)
+    return ctx._wrap_pinned(p_ids.value, (k,), np.int64), ctx._wrap_pinned(p_out.value, (k, total), np.float64)
 
 
 def build_csr(ctx, ids, sort_keys, values):

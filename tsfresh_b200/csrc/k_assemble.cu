@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(WPC * 32) k_assemble(AssembleArgs A, int row_p
             for (int j = lane; j < w; j += 32) row[__ldg(A.final_col + c0 + j)] = __ldcs(src + j);
         }
         __syncwarp();
-        const size_t roff = (size_t)s * A.ncols;
+        const size_t roff = (size_t)s * A.ld;
         if (A.out_mc) {
             double* dst = A.out_mc + roff;
             for (int j = lane; j < A.ncols; j += 32)

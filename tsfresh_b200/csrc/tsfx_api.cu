@@ -241,6 +241,7 @@ struct tsfx_ctx {
     int64_t held_series = -1;    // CSR kept on the device by the last stage-(a) call (-1: none)
     int held_max_len = 0;
     bool used_moments = false;   // the last pass ran k_moments in place of k_basic (reported as "moments")
+    DevBuf kvals, kvals_sorted;  // value columns of kinds 1 .. K-1 of a wide frame (input order / CSR order)
     DevBuf times, times_sorted;  // tsfx_set_row_times: row timestamps of the next extract call (linear_trend_timewise)
     const int64_t* times_ptr = nullptr;
     int64_t times_rows = -1;
@@ -386,7 +387,7 @@ extern "C" void tsfx_ctx_destroy(tsfx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->values.release(); ctx->begin.release(); ctx->len.release(); ctx->out.release(); ctx->misc.release(); ctx->stage.release();
-    ctx->times.release(); ctx->times_sorted.release();
+    ctx->times.release(); ctx->times_sorted.release(); ctx->kvals.release(); ctx->kvals_sorted.release();
     ctx->csr.release();
     ctx->imp.release();
     ctx->sel.release();
@@ -598,7 +599,8 @@ extern "C" int tsfx_set_row_times(tsfx_ctx* ctx, const int64_t* row_time_ns, int
     return TSFX_OK;
 }
 
-static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int max_len, double* d_out, uint32_t flags) {
+static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int max_len, double* d_out, uint32_t flags, int ld = 0) {
+    if (ld <= 0) ld = P->ncols;          // row stride of the caller's matrix
     const bool timing = (flags & TSFX_FLAG_TIMING) != 0;
     for (int g = 0; g < G_EVENTS; ++g) ctx->ev_used[g] = false;
     ctx->launches = 0;
@@ -652,7 +654,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                     M.R = R; M.descs = P->dev[g]; M.nd = g_ncols; M.need_high = P->moments_need_high;
                     direct = (P->n_groups_used == 1) && ctx->peer_out.empty() && (P->ncols == g_ncols);
                     M.out = direct ? d_final : d_out;
-                    M.ncols = direct ? P->ncols : g_ncols;
+                    M.ncols = direct ? ld : g_ncols;
                     M.colmap = direct ? P->d_final_col + P->cum[g] : nullptr;
                     e = launch_moments(M, gs, ctx->sm_count);
                     ctx->used_moments = true;
@@ -746,7 +748,8 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
     if (!direct) {   // scatter the staging matrices into the caller's [n_series x ncols] matrix
         if (timing) { CK(cudaEventRecord(ctx->ev[G_COUNT][0], ctx->stream)); }
         AssembleArgs A;
-        A.stage = (const double*)ctx->stage.p; A.out = d_final; A.n_series = R.n_series; A.ncols = P->ncols;
+        A.stage = (const double*)ctx->stage.p; A.out = d_final; A.n_series = R.n_series; A.ncols = P->ncols; A.ld = ld;
+        if (ld != P->ncols && !ctx->peer_out.empty()) return fail(ctx, TSFX_E_UNSUPPORTED, "peer placement of a strided matrix");
         A.n_groups = G_COUNT;
         for (int g = 0; g <= G_COUNT; ++g) A.cum[g] = P->cum[g];
         A.final_col = P->d_final_col;
@@ -979,10 +982,15 @@ struct LongIn {
     const int64_t* ids;
     const void* keys;
     int is_f64;
-    const float* values;
+    const float* values;           // value column of kind 0
     int64_t n;
     bool device;
+    const float* const* more = nullptr;   // value columns of kinds 1 .. n_kinds-1 (wide format: the kinds share ids and sort keys)
+    int n_kinds = 1;
+    const float* col(int k) const { return k == 0 ? values : more[k - 1]; }
 };
+
+static inline size_t kind_stride(int64_t n) { return ((size_t)n + 3) & ~(size_t)3; }   // floats between the kinds' device columns
 
 static int nan_error(tsfx_ctx* ctx) { return fail(ctx, TSFX_E_NAN, "the value column contains NaN"); }
 
@@ -1085,14 +1093,25 @@ extern "C" int tsfx_build_csr(tsfx_ctx* ctx, const int64_t* ids, const void* sor
     return TSFX_OK;
 }
 
+// the kinds of one call: plan, device value column (CSR order) and first output column of each
+#define TSFX_MAX_KINDS 64
+struct KindSet {
+    int n = 1;
+    const tsfx_plan* plan[TSFX_MAX_KINDS];
+    const float* dvals[TSFX_MAX_KINDS];
+    int col0[TSFX_MAX_KINDS];
+    int total_cols = 0;
+};
+
 // kernels + result transfer over the row blocks of a device CSR.  stream_in: the key / value rows of a block are
 // copied from the host right before the block's kernels (fast path); d_out == nullptr: results go through ctx->out
-// and are copied to `out` (host) block by block on the D2H stream.
-static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info, const LongIn* stream_in,
-                      const int64_t* d_ids, const uint64_t* d_keys, const float* d_vals, bool check_rows, bool check_nan,
+// and are copied to `out` (host) block by block on the D2H stream.  Several kinds (wide format) share the CSR: every
+// block runs each kind's plan on that kind's value column and writes its own column block of the one result matrix.
+static int run_blocks(tsfx_ctx* ctx, const KindSet& K, const CsrInfo& info, const LongIn* stream_in,
+                      const int64_t* d_ids, const uint64_t* d_keys, bool check_rows, bool check_nan,
                       double* out, bool out_is_device, uint32_t flags, const int64_t* row_times = nullptr) {
     CsrWorkspace& W = ctx->csr;
-    const size_t ncols = (size_t)plan->ncols;
+    const size_t ncols = (size_t)K.total_cols;
     const int64_t ns = info.n_series;
     double* dout = out;
     if (!out_is_device) {
@@ -1106,16 +1125,23 @@ static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info,
         const int slot = b & 1;
         if (stream_in) {
             if (stream_in->keys) CK(ctx->stager.h2d(W.keys() + r0, (const uint64_t*)stream_in->keys + r0, (size_t)(r1 - r0) * 8, ctx->s_in));
-            CK(ctx->stager.h2d(W.vals() + r0, stream_in->values + r0, (size_t)(r1 - r0) * 4, ctx->s_in));
+            for (int k = 0; k < K.n; ++k)
+                CK(ctx->stager.h2d(const_cast<float*>(K.dvals[k]) + r0, stream_in->col(k) + r0, (size_t)(r1 - r0) * 4, ctx->s_in));
             CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
         }
-        if (check_rows) csr_check_rows(W, d_ids, d_keys, stream_in ? stream_in->is_f64 : 0, d_vals, r0, r1, check_nan, ctx->stream);
-        SeriesRef R;
-        R.values = W.d_values; R.begin = W.d_begin + s0; R.len = W.d_len + s0; R.dense_len = 0; R.n_series = s1 - s0;
-        R.times = row_times;
-        int rc = run_groups(ctx, plan, R, info.max_len, dout + (size_t)s0 * ncols, flags);
-        if (rc) return rc;
+        if (check_rows) {
+            csr_check_rows(W, d_ids, d_keys, stream_in ? stream_in->is_f64 : 0, K.dvals[0], r0, r1, check_nan, ctx->stream);
+            if (check_nan) for (int k = 1; k < K.n; ++k) csr_check_nan(W, K.dvals[k] + r0, r1 - r0, ctx->stream);
+        }
+        for (int k = 0; k < K.n; ++k) {
+            if (K.plan[k]->ncols == 0) continue;
+            SeriesRef R;
+            R.values = K.dvals[k]; R.begin = W.d_begin + s0; R.len = W.d_len + s0; R.dense_len = 0; R.n_series = s1 - s0;
+            R.times = row_times;
+            int rc = run_groups(ctx, K.plan[k], R, info.max_len, dout + (size_t)s0 * ncols + K.col0[k], flags, K.total_cols);
+            if (rc) return rc;
+        }
         if (impute || out_is_device) continue;
         CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[slot], 0));
@@ -1123,17 +1149,32 @@ static int run_blocks(tsfx_ctx* ctx, const tsfx_plan* plan, const CsrInfo& info,
                            cudaMemcpyDeviceToHost, ctx->s_out));
     }
     if (impute) {
-        int rc = impute_after_extract(ctx, dout, ns, plan->ncols);
+        int rc = impute_after_extract(ctx, dout, ns, K.total_cols);
         if (rc) return rc;
         if (!out_is_device) CK(cudaMemcpyAsync(out, dout, (size_t)ns * ncols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return TSFX_OK;
 }
 
-static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn& in, int64_t* out_ids, double* out,
+static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* const* plans, const LongIn& in, int64_t* out_ids, double* out,
                              int64_t out_capacity, int64_t** out_ids_alloc, double** out_alloc, int64_t* n_series_out,
                              uint32_t flags) {
     CsrWorkspace& W = ctx->csr;
+    const tsfx_plan* plan = plans[0];
+    KindSet K;
+    K.n = in.n_kinds;
+    if (K.n < 1 || K.n > TSFX_MAX_KINDS) return fail(ctx, TSFX_E_INVALID, "between 1 and 64 kinds per call");
+    bool any_times = false;
+    for (int k = 0; k < K.n; ++k) {
+        if (!plans[k] || plans[k]->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
+        K.plan[k] = plans[k];
+        K.col0[k] = K.total_cols;
+        K.total_cols += plans[k]->ncols;
+        any_times = any_times || plans[k]->need_times;
+    }
+    for (int k = 0; k < K.n; ++k) if (plans[k]->need_times) plan = plans[k];      // take_times looks at one plan's flag
+    const size_t kstride = kind_stride(in.n);
+    if (K.n > 1 && !in.device) CK(ctx->kvals.reserve((size_t)(K.n - 1) * kstride * 4 + 16));
     const bool check_nan = !(flags & TSFX_FLAG_NO_NAN_CHECK);
     const int max_blocks = (flags & TSFX_FLAG_TIMING) ? 1 : 16;
     ctx->held_series = -1;
@@ -1146,15 +1187,38 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn&
     rc = stage_a(ctx, in, max_blocks, check_nan, &info, &streamed, &d_ids, &d_keys, &d_vals);
     if (rc) return rc;
     bool sorted = !info.unsorted_ids;
+    bool extra_resident = in.device;              // value columns of kinds 1.. are on the device in input order
+    auto extra_in = [&](int k) -> const float* {  // device column of kind k >= 1, input row order
+        return in.device ? in.col(k) : (const float*)ctx->kvals.p + (size_t)(k - 1) * kstride;
+    };
+    if (sorted && in.device && check_nan)
+        for (int k = 1; k < K.n; ++k) csr_check_nan(W, in.col(k), in.n, ctx->stream);
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!sorted) {
             rc = stage_a_sort(ctx, in, max_blocks, check_nan, &info, d_ids, d_keys, d_vals);
             if (rc) return rc;
             if (info.has_nan) return nan_error(ctx);
         }
+        // device value column of every kind in CSR order
+        K.dvals[0] = W.d_values;
+        if (K.n > 1) {
+            if (W.d_perm) {                       // rows were sorted on the device: the other kinds follow the permutation
+                CK(ctx->kvals_sorted.reserve((size_t)(K.n - 1) * kstride * 4 + 16));
+                for (int k = 1; k < K.n; ++k) {
+                    if (!extra_resident) CK(ctx->stager.h2d(const_cast<float*>(extra_in(k)), in.col(k), (size_t)in.n * 4, ctx->stream));
+                    if (check_nan) csr_check_nan(W, extra_in(k), in.n, ctx->stream);
+                    float* dst = (float*)ctx->kvals_sorted.p + (size_t)(k - 1) * kstride;
+                    csr_gather_f32(W, extra_in(k), dst, in.n, ctx->stream);
+                    K.dvals[k] = dst;
+                }
+                extra_resident = true;
+            } else {
+                for (int k = 1; k < K.n; ++k) K.dvals[k] = extra_in(k);
+            }
+        }
         const int64_t ns = info.n_series;
         *n_series_out = ns;
-        const size_t ob = (size_t)ns * plan->ncols * sizeof(double);
+        const size_t ob = (size_t)ns * K.total_cols * sizeof(double);
         if (out_alloc) {                         // library-sized result from the pinned pool
             if (!*out_alloc) {
                 *out_alloc = (double*)ctx->pool.alloc(std::max<size_t>(ob, 8));
@@ -1174,8 +1238,9 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn&
             csr_gather_i64(W, times_in, (int64_t*)ctx->times_sorted.p, in.n, ctx->stream);
             row_times = (const int64_t*)ctx->times_sorted.p;
         }
-        rc = run_blocks(ctx, plan, info, (first_sorted_try && streamed) ? &in : nullptr, d_ids, d_keys, d_vals,
+        rc = run_blocks(ctx, K, info, (first_sorted_try && streamed) ? &in : nullptr, d_ids, d_keys,
                         /*check_rows=*/first_sorted_try && streamed, check_nan, out, in.device, flags, row_times);
+        if (first_sorted_try && streamed) extra_resident = true;
         if (rc) return rc;
         if (out_ids) CK(cudaMemcpyAsync(out_ids, W.d_uid, (size_t)ns * sizeof(int64_t), in.device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         if (in.device && !first_sorted_try) break;                       // asynchronous contract: nothing to wait for
@@ -1191,6 +1256,7 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* plan, const LongIn&
             LongIn dev{d_ids, d_keys, in.is_f64, d_vals, in.n, true};
             rc = stage_a_sort(ctx, dev, max_blocks, check_nan, &info, d_ids, d_keys, d_vals);
             if (rc) return rc;
+            if (info.has_nan) return nan_error(ctx);
             sorted = true;                        // CSR rebuilt: second trip only runs the kernels
             streamed = false;
         }
@@ -1221,7 +1287,9 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
         CsrInfo info = {};
         info.n_series = ns; info.max_len = ctx->held_max_len; info.n_blocks = 1;
         info.series_lo[0] = 0; info.series_lo[1] = ns; info.row_lo[0] = 0; info.row_lo[1] = 0;
-        int rc = run_blocks(ctx, plan, info, nullptr, nullptr, nullptr, nullptr, false, false, out, false, flags);
+        KindSet K1;
+        K1.plan[0] = plan; K1.dvals[0] = ctx->csr.d_values; K1.col0[0] = 0; K1.total_cols = plan->ncols;
+        int rc = run_blocks(ctx, K1, info, nullptr, nullptr, nullptr, false, false, out, false, flags);
         if (rc) return rc;
         if (out_ids) CK(cudaMemcpyAsync(out_ids, ctx->csr.d_uid, ns * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->s_out));
@@ -1230,7 +1298,7 @@ extern "C" int tsfx_extract_long(tsfx_ctx* ctx, const tsfx_plan* plan, const int
     }
     if (n_rows == 0) return TSFX_OK;
     LongIn in{ids, sort_keys, sort_key_is_f64, values, n_rows, (flags & TSFX_FLAG_DEVICE_PTRS) != 0};
-    return extract_long_impl(ctx, plan, in, out_ids, out, out_capacity, nullptr, nullptr, n_series_out, flags);
+    return extract_long_impl(ctx, &plan, in, out_ids, out, out_capacity, nullptr, nullptr, n_series_out, flags);
 }
 
 extern "C" int tsfx_extract_long_alloc(tsfx_ctx* ctx, const tsfx_plan* plan, const int64_t* ids, const void* sort_keys,
@@ -1247,7 +1315,34 @@ extern "C" int tsfx_extract_long_alloc(tsfx_ctx* ctx, const tsfx_plan* plan, con
     *out_ids = nullptr;
     if (n_rows == 0) return TSFX_OK;
     LongIn in{ids, sort_keys, sort_key_is_f64, values, n_rows, false};
-    int rc = extract_long_impl(ctx, plan, in, nullptr, nullptr, 0, out_ids, out, n_series_out, flags);
+    int rc = extract_long_impl(ctx, &plan, in, nullptr, nullptr, 0, out_ids, out, n_series_out, flags);
+    if (rc) {
+        if (*out) ctx->pool.free(*out);
+        if (*out_ids) ctx->pool.free(*out_ids);
+        *out = nullptr; *out_ids = nullptr;
+    }
+    return rc;
+}
+
+extern "C" int tsfx_extract_long_kinds(tsfx_ctx* ctx, const tsfx_plan* const* plans, const int64_t* ids, const void* sort_keys,
+                                       int32_t sort_key_is_f64, const float* const* values, int32_t n_kinds, int64_t n_rows,
+                                       int64_t** out_ids, double** out, int64_t* n_series_out, uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (flags & TSFX_FLAG_DEVICE_PTRS) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long_kinds takes host pointers");
+    if (n_kinds < 1 || n_kinds > TSFX_MAX_KINDS || !plans || !values || n_rows < 0 || !n_series_out || !out || !out_ids ||
+        (n_rows > 0 && !ids))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long_kinds: bad arguments");
+    for (int k = 0; k < n_kinds; ++k)
+        if (!plans[k] || (n_rows > 0 && !values[k])) return fail(ctx, TSFX_E_INVALID, "tsfx_extract_long_kinds: NULL plan / column");
+    CK(cudaSetDevice(ctx->device));
+    *n_series_out = 0;
+    *out = nullptr;
+    *out_ids = nullptr;
+    if (n_rows == 0) return TSFX_OK;
+    LongIn in{ids, sort_keys, sort_key_is_f64, values[0], n_rows, false};
+    in.more = values + 1;
+    in.n_kinds = n_kinds;
+    int rc = extract_long_impl(ctx, plans, in, nullptr, nullptr, 0, out_ids, out, n_series_out, flags);
     if (rc) {
         if (*out) ctx->pool.free(*out);
         if (*out_ids) ctx->pool.free(*out_ids);

@@ -164,6 +164,14 @@ __global__ void k_gather_i64(const int64_t* __restrict__ src, const uint32_t* __
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = src[perm[i]];
 }
+__global__ void k_gather_f32(const float* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n, float* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[perm[i]];
+}
+void csr_gather_f32(CsrWorkspace& W, const float* src, float* dst, int64_t n, cudaStream_t st) {
+    if (n > 0 && W.d_perm) k_gather_f32<<<grid_for(n, 256), 256, 0, st>>>(src, W.d_perm, n, dst);
+}
 void csr_gather_i64(CsrWorkspace& W, const int64_t* src, int64_t* dst, int64_t n, cudaStream_t st) {
     if (n > 0 && W.d_perm) k_gather_i64<<<grid_for(n, 256), 256, 0, st>>>(src, W.d_perm, n, dst);
 }

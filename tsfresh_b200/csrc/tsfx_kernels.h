@@ -83,7 +83,8 @@ struct AssembleArgs {
     const double* stage;          // group g starts at stage + n_series * cum[g]
     double* out;
     int64_t n_series;
-    int ncols;                    // final row stride
+    int ncols;                    // columns of this plan
+    int ld;                       // row stride of `out` (>= ncols: several kinds share one matrix, each its own column block)
     int n_groups;
     int cum[G_COUNT + 1];         // columns before group g (cum[n_groups] = total staged columns)
     const int32_t* final_col;     // device: final column of staged column (cum[g] + j)

@@ -135,9 +135,10 @@ def _frames(container, column_id, column_kind, column_value, column_sort):
             _check_colname(*value_columns)
             if column_sort is not None:
                 _check_nan(df, column_sort)
-            for kind in value_columns:
-                out.append((kind, df[column_id], df[column_sort] if column_sort is not None else None, df[kind],
-                            isinstance(df.index, pd.DatetimeIndex)))
+            id_col = df[column_id]
+            sort_col = df[column_sort] if column_sort is not None else None
+            for kind in value_columns:         # the SAME id / sort objects for every kind: extract_features detects the wide format by it
+                out.append((kind, id_col, sort_col, df[kind], isinstance(df.index, pd.DatetimeIndex)))
             id_dtype = df[column_id].dtype
     elif isinstance(container, dict):                                # dict of frames (data.py:294-338)
         _check_colname(*list(container.keys()))
@@ -314,6 +315,36 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
     codes, decoder = _encode_ids([f[1] for f in frames])
 
     blocks = []           # (column names, ids (codes), matrix)
+    # wide format (several value columns of ONE frame share the id / sort columns): the kind dimension lives in the device
+    # pass -- one stage (a), one result matrix with a column block per kind (tsfx_extract_long_kinds)
+    shared = len(frames) > 1 and pivot and all(f[1] is frames[0][1] and f[2] is frames[0][2] for f in frames[1:])
+    if shared:
+        plans, names = [], []
+        for kind, _ids, sort_col, values, has_dt in frames:
+            fc = kind_to_fc_parameters[kind] if (kind_to_fc_parameters and kind in kind_to_fc_parameters) else default_fc_parameters
+            plan = Plan(fc, has_datetime_index=has_dt)
+            if show_warnings:
+                for name in plan.skipped:
+                    warnings.warn("{} requires the data to have a index of type {}. Results will "
+                                  "not be calculated".format(name, pd.DatetimeIndex))
+            plans.append(plan)
+            names += [str(kind) + "__" + sfx for sfx in plan.suffixes]
+        if len(codes[0]) and all(p.n_cols > 0 for p in plans):
+            dps = [_device_plan(ctx, p) for p in plans]
+            times = frames[0][3].index.as_unit("ns").asi8 if any(p.needs_times for p in plans) else None
+            flags_k = _lib.FLAG_IMPUTE if device_impute else 0
+            try:
+                uid, mat = _lib.extract_long_kinds(ctx, dps, codes[0], _sort_keys(frames[0][2]),
+                                                   [f[3].to_numpy().astype(np.float32, copy=False) for f in frames], flags=flags_k,
+                                                   times=times)
+            except ValueError as e:
+                if "contains NaN" in str(e):
+                    raise ValueError("Column must not contain NaN values: {}".format(
+                        ", ".join(str(f[3].name) for f in frames))) from None
+                raise
+            blocks.append((names, uid, mat))
+            frames, codes = [], []
+            extract_flags = flags_k
     for (kind, _ids, sort_col, values, has_dt), id_codes in zip(frames, codes):
         if kind_to_fc_parameters and kind in kind_to_fc_parameters:
             fc = kind_to_fc_parameters[kind]
