@@ -209,7 +209,7 @@ __device__ __forceinline__ bool friedrich_fit(const float* xs, const float* srt,
 }
 
 template <int WPC, bool GS>
-__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : 1)) k_sorted(SortedArgs A) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 8 ? 3 : (WPC == 12 ? 2 : 1))) k_sorted(SortedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = warp_region<GS>(smem_raw, A.gscratch, A.bytes_per_warp, WPC, warp);
@@ -416,6 +416,21 @@ cudaError_t launch_sorted(const SortedArgs& A0, int max_len, cudaStream_t st, in
     Geometry G;
     if (!plan_geometry(per, 100 * 1024, 8, A.R.n_series, sm_count, A.gscratch, A.gscratch_bytes, &G)) return cudaErrorInvalidConfiguration;
     A.gscratch = G.gscratch;
+    {
+        // TSFX_SORTED_WPC=12: two CTAs of 12 warps per SM instead of three of 8 (same idea as k_basic: the lock-step walk
+        // shares the instruction stream inside a CTA)
+        static int wide = -1;
+        if (wide < 0) { const char* e = getenv("TSFX_SORTED_WPC"); wide = e ? atoi(e) : 0; }
+        if (wide == 12 && !G.gscratch && G.wpc == 8 && per * 12 <= 113 * 1024) {
+            const size_t smem = per * 12;
+            const int64_t ctas = (A.R.n_series + 11) / 12;
+            const int64_t cap = (int64_t)sm_count * grid_waves(4096);
+            cudaError_t e = cudaFuncSetAttribute(k_sorted<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            k_sorted<12, false><<<(int)std::max<int64_t>(1, std::min(ctas, cap)), 12 * 32, smem, st>>>(A);
+            return cudaGetLastError();
+        }
+    }
     TSFX_DISPATCH(k_sorted, G, st, A)
     return cudaGetLastError();
 }

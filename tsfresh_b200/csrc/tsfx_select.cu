@@ -95,7 +95,7 @@ __global__ void k_sel_runs(const double* __restrict__ keys, const uint32_t* __re
         const double v = keys[i];
         const int64_t a = i;
         const unsigned long long ones_a = ones;
-        while (i < n && keys[i] == v) { ones += y[rows[i]] == cls; ++i; }
+        do { ones += y[rows[i]] == cls; ++i; } while (i < n && keys[i] == v);      // always advances (a NaN key equals nothing)
         const double t = (double)(i - a), c1 = (double)(ones - ones_a);
         const double z_before = (double)a - (double)ones_a;
         u1 += c1 * (z_before + 0.5 * (t - c1));
