@@ -170,6 +170,7 @@ void tsfx_ctx_destroy(tsfx_ctx* ctx);
 const char* tsfx_last_error(const tsfx_ctx* ctx); /* ctx may be NULL: last creation error */
 int tsfx_sync(tsfx_ctx* ctx);
 int tsfx_version(void);
+int tsfx_device_count(void);   /* CUDA devices visible to this process (0 when there is none) */
 
 /* Plan: the compiled settings dict.  `tables` holds the concatenated float64 convolution kernels for
  * cwt_coefficients (one per distinct scale, table t = tables[table_off[t] .. table_off[t+1])),

@@ -79,3 +79,24 @@ def test_world_size_2_every_rank_holds_the_full_matrix(mode):
         ok1, ok2, kind, placement = ret[r]
         assert ok1, (r, kind, placement)
         assert ok2, (r, kind, placement)
+
+
+def test_n_jobs_drives_several_gpus_from_one_process():
+    """extract_features(n_jobs=2): the frame is cut at id boundaries, each GPU fills its rows of one pinned matrix"""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import pandas as pd
+    from tsfresh_b200 import MinimalFCParameters, extract_features
+    rng = np.random.default_rng(3)
+    S, L = 24_000, 64                                   # 1.5 M rows: above the multi-GPU threshold
+    df = pd.DataFrame({"id": np.repeat(np.arange(S, dtype=np.int64) * 3, L), "time": np.tile(np.arange(L, dtype=np.int64), S),
+                       "value": rng.standard_normal(S * L).astype(np.float32)})
+    one = extract_features(df, column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters(), n_jobs=1)
+    two = extract_features(df, column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters(), n_jobs=2)
+    assert list(one.index) == list(two.index) and list(one.columns) == list(two.columns)
+    assert np.array_equal(one.to_numpy(), two.to_numpy(), equal_nan=True)
+    # rows out of order: falls back to one GPU (device sort), same frame
+    shuffled = df.sample(frac=1.0, random_state=0)
+    three = extract_features(shuffled, column_id="id", column_sort="time", default_fc_parameters=MinimalFCParameters(), n_jobs=2)
+    assert np.array_equal(one.to_numpy(), three.to_numpy(), equal_nan=True) and list(one.index) == list(three.index)

@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification", "tsfx_extract_long_kinds"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification", "tsfx_extract_long_kinds", "tsfx_device_count"]
 
 
 def load():
@@ -76,6 +76,10 @@ def load():
                                                 ctypes.POINTER(i64), u32]
         _lib = lib
         return lib
+
+
+def device_count():
+    return int(load().tsfx_device_count())
 
 
 def _ptr(a):
@@ -269,6 +273,19 @@ class DevicePlan:
         if k == 0 or not p_out.value:
             return np.empty(0, dtype=np.int64), np.empty((0, self.n_cols), dtype=np.float64)
         return ctx._wrap_pinned(p_ids.value, (k,), np.int64), ctx._wrap_pinned(p_out.value, (k, self.n_cols), np.float64)
+
+    def extract_long_into(self, ids, sort_keys, values, out_ids, out, flags=0):
+        """tsfx_extract_long into caller buffers (rows of a larger pinned matrix): returns the number of series written"""
+        is_f64 = 0
+        if sort_keys is not None and sort_keys.dtype.kind == "f":
+            is_f64 = 1
+        n_series = ctypes.c_int64(0)
+        ctx = self.ctx
+        with ctx.lock:
+            rc = ctx.lib.tsfx_extract_long(ctx.h, self.h, _ptr(ids), _ptr(sort_keys), is_f64, _ptr(values), len(ids), _ptr(out_ids),
+                                           _ptr(out), len(out), ctypes.byref(n_series), flags)
+            ctx.check(rc, "tsfx_extract_long")
+        return n_series.value
 
     # ---- device-pointer entry points (torch tensors own the memory) ----------------------------
     def extract_dense_device(self, values_ptr, n_series, length, out_ptr, timing=False):

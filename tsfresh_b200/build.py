@@ -20,8 +20,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 def _digest(paths):
     h = hashlib.sha256()
-    for p in sorted(paths):
-        h.update(p.encode())
+    for p in sorted(paths, key=os.path.basename):
+        h.update(os.path.basename(p).encode())      # not the absolute path: the stamp must stay valid when the tree is copied
         h.update(open(p, "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()

@@ -20,6 +20,7 @@ namespace tsfx {
 struct SeqLayout {
     int hot_bytes, hot_lines, hot_map, hot_bits;     // k_peaks from the global working region: the small, latency-critical
                                                      // tables (ridge lines, column map, maxima bits) stay in shared memory
+    int hist_cap;                                    // permutation-histogram bins the `codes` area can hold
     int npad, npow2, nwords, lz_lanes, cwt_n, lz_hash, lz_stride, nxd;
     int off_rowsf, off_noise, off_hw, off_codes, off_trie, off_sym, off_bits, off_lines, off_map, off_xs, off_xd;   // byte offsets
 };
@@ -169,8 +170,14 @@ __device__ __forceinline__ unsigned pe_lehmer(unsigned bits, int D) {
     return code;            // digit D-1 is always 0 (radix 1)
 }
 
-template <int WPC, bool GS>
-__global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
+// SMALL = compact shared-memory working set for series of at most 256 samples and alphabets of at most 127 symbols (the
+// BASELINE shapes): byte symbols, 16-bit trie keys (node << 7 | symbol, 256 slots per parse) and permutation histograms
+// with two 16-bit counters per word -- 6.5 KB per warp, so 32 warps per SM run entirely from shared memory.  The general
+// layout (uint32 keys, uint16 symbols, uint32 counters) needs 17.8 KB per warp and runs from the global working region,
+// where every probe of the sequential parse and every histogram update is an L2 round trip (ncu: long_scoreboard 5.2
+// stalls per issued instruction).
+template <int WPC, bool GS, bool SMALL>
+__device__ __forceinline__ void seq_body(const SeqArgs& A, const SeqLayout& Y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double clogc_small[64];            // c ln c for small counts (permutation histograms are mostly tiny)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
     unsigned* codes = reinterpret_cast<unsigned*>(base + Y.off_codes);
     unsigned short* trie = reinterpret_cast<unsigned short*>(base + Y.off_trie);
     unsigned short* symbuf = reinterpret_cast<unsigned short*>(base + Y.off_sym);
+    unsigned char* symbuf8 = base + Y.off_sym;
     float* xs = reinterpret_cast<float*>(base + Y.off_xs);
     const int64_t warps_total = (int64_t)gridDim.x * WPC;
 
@@ -201,32 +209,53 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                 for (int q = 0; q < cnt; ++q) {                      // symbols of every position, all lanes
                     const int bins = A.descs[j + q].i0;
                     const double step = __ddiv_rn(__dsub_rn(vmax, vmin), (double)bins);
-                    unsigned short* sb = symbuf + (size_t)q * Y.npad;
-                    for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                    if (SMALL) {
+                        unsigned char* sb = symbuf8 + (size_t)q * Y.npad;
+                        for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned char)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                    } else {
+                        unsigned short* sb = symbuf + (size_t)q * Y.npad;
+                        for (int pos = lane; pos < n; pos += 32) sb[pos] = (unsigned short)lz_symbol((double)xs[pos], vmin, vmax, step, bins);
+                    }
                 }
                 __syncwarp();
                 // phrase dictionary = prefix-closed trie stored as ONE open-addressing table of keys
                 // (parent slot << 16 | symbol); a node's id is the slot its key lives in, the root is 0xffff
                 {
-                    unsigned* tab = reinterpret_cast<unsigned*>(trie);
-                    for (int q = lane; q < cnt * Y.lz_hash; q += 32) tab[q] = 0xffffffffu;
+                    unsigned* tab = reinterpret_cast<unsigned*>(trie);       // SMALL: two 16-bit keys per word
+                    const int words = SMALL ? (cnt * Y.lz_hash) >> 1 : cnt * Y.lz_hash;
+                    for (int q = lane; q < words; q += 32) tab[q] = 0xffffffffu;
                 }
                 __syncwarp();
                 if (lane < cnt) {
                     const Desc d = A.descs[j + lane];
-                    const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
-                    unsigned* hkey = reinterpret_cast<unsigned*>(trie) + (size_t)lane * Y.lz_hash;
-                    const unsigned mask = (unsigned)Y.lz_hash - 1u;
-                    unsigned node = 0xffffu;
                     int phrases = 0;
-                    for (int pos = 0; pos < n; ++pos) {
-                        const unsigned key = (node << 16) | (unsigned)sb[pos];
-                        unsigned h = (key * 0x9E3779B1u) >> 15;
-                        h &= mask;
-                        unsigned k;
-                        while ((k = hkey[h]) != key && k != 0xffffffffu) h = (h + 1u) & mask;
-                        if (k == key) node = h;                      // phrase seen: extend it
-                        else { hkey[h] = key; ++phrases; node = 0xffffu; }
+                    if (SMALL) {
+                        const unsigned char* sb = symbuf8 + (size_t)lane * Y.npad;
+                        unsigned short* hkey = trie + (size_t)lane * Y.lz_hash;
+                        const unsigned mask = (unsigned)Y.lz_hash - 1u;          // 256 slots: node ids fit 8 bits, the root is 256
+                        unsigned node = 256u;
+                        for (int pos = 0; pos < n; ++pos) {
+                            const unsigned key = (node << 7) | (unsigned)sb[pos];
+                            unsigned h = ((key * 0x9E3779B1u) >> 20) & mask;
+                            unsigned k;
+                            while ((k = hkey[h]) != key && k != 0xffffu) h = (h + 1u) & mask;
+                            if (k == key) node = h;
+                            else { hkey[h] = (unsigned short)key; ++phrases; node = 256u; }
+                        }
+                    } else {
+                        const unsigned short* sb = symbuf + (size_t)lane * Y.npad;
+                        unsigned* hkey = reinterpret_cast<unsigned*>(trie) + (size_t)lane * Y.lz_hash;
+                        const unsigned mask = (unsigned)Y.lz_hash - 1u;
+                        unsigned node = 0xffffu;
+                        for (int pos = 0; pos < n; ++pos) {
+                            const unsigned key = (node << 16) | (unsigned)sb[pos];
+                            unsigned h = (key * 0x9E3779B1u) >> 15;
+                            h &= mask;
+                            unsigned k;
+                            while ((k = hkey[h]) != key && k != 0xffffffffu) h = (h + 1u) & mask;
+                            if (k == key) node = h;                      // phrase seen: extend it
+                            else { hkey[h] = key; ++phrases; node = 0xffffu; }
+                        }
                     }
                     orow[d.col] = (double)phrases / (double)n;
                 }
@@ -242,14 +271,19 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                     if (D <= 6) {
                         int f = 1;
                         for (int q = 2; q <= D; ++q) f *= q;
-                        if (bins_total + f > Y.npow2) break;
+                        if (bins_total + f > Y.hist_cap) break;
                         bins_total += f;
                         Dh = max(Dh, D);
                     }
                     ++cnt;
                 }
+                if (cnt == 0) {             // a histogram that does not fit the `codes` area at all: cannot happen for
+                    if (lane == 0) orow[d0.col] = dnan();      // dimensions <= 6 (720 bins <= hist_cap); never loop in place
+                    ++j;
+                    continue;
+                }
                 if (Dh > 0) {
-                    for (int b = lane; b < bins_total; b += 32) codes[b] = 0u;
+                    for (int b = lane; b < (SMALL ? (bins_total + 1) >> 1 : bins_total); b += 32) codes[b] = 0u;
                     __syncwarp();
                     const int Wmax = (n >= 2) ? (n - 2) / tau + 1 : 0;          // windows of the smallest dimension
                     for (int k = lane; k < Wmax; k += 32) {
@@ -261,7 +295,11 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                             if (D > 6) continue;
                             int f = 1;
                             for (int q = 2; q <= D; ++q) f *= q;
-                            if (st + D <= n) atomicAdd(&codes[off + pe_lehmer(bits, D)], 1u);
+                            if (st + D <= n) {
+                                const unsigned bin = off + pe_lehmer(bits, D);
+                                if (SMALL) atomicAdd(&codes[bin >> 1], (bin & 1u) ? 0x10000u : 1u);
+                                else atomicAdd(&codes[bin], 1u);
+                            }
                             off += f;
                         }
                     }
@@ -279,7 +317,7 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
                             // -sum p ln p = ln W - (1/W) sum c ln c  (bins with c = 1 contribute nothing)
                             double acc = 0.0;
                             for (int b = lane; b < f; b += 32) {
-                                const unsigned c = codes[off + b];
+                                const unsigned c = SMALL ? (codes[(off + b) >> 1] >> (16 * ((off + b) & 1))) & 0xffffu : codes[off + b];
                                 if (c > 1u) acc += c < 64u ? clogc_small[c] : (double)c * log((double)c);
                             }
                             r = log((double)W) - wsum(acc) / (double)W;
@@ -325,6 +363,12 @@ __global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) {
         __syncwarp();
     }
 }
+
+template <int WPC, bool GS>
+__global__ void __launch_bounds__(WPC * 32) k_seq(SeqArgs A, SeqLayout Y) { seq_body<WPC, GS, false>(A, Y); }
+
+template <int WPC, bool GS>
+__global__ void __launch_bounds__(WPC * 32, (WPC == 4 ? 8 : 1)) k_seq_small(SeqArgs A, SeqLayout Y) { seq_body<WPC, GS, true>(A, Y); }
 
 template <int WPC, bool GS>
 __global__ void __launch_bounds__(WPC * 32) k_peaks(SeqArgs A, SeqLayout Y) {
@@ -526,11 +570,41 @@ cudaError_t launch_seq(const SeqArgs& A0, int max_len, cudaStream_t st, int sm_c
     int p2 = 2;
     while (p2 < max_len) p2 <<= 1;
     Y.npow2 = std::max(p2, 1024);                 // >= 6! = 720 so dimensions up to 6 use the histogram path
+    Y.hist_cap = Y.npow2;
     const bool need_lz = (A.nscr & 1) != 0, need_perm = (A.nscr & 2) != 0;
     Y.lz_lanes = need_lz ? std::min(LZ_LANES, std::max(1, (A.nscr >> 16) & 0xff)) : 0;
     Y.lz_hash = 4;
     while (Y.lz_hash < A.npad + A.npad / 2 + 2) Y.lz_hash <<= 1;      // load factor <= 2/3 in the worst case
     Y.lz_stride = 2 * Y.lz_hash;                  // uint16 units: one uint32 key per slot
+    {
+        // compact shared-memory layout (k_seq_small): TSFX_SEQ=general keeps the general kernel for A/B runs
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("TSFX_SEQ"); mode = (e && e[0] == 'g') ? 0 : 1; }
+        const int max_bins = (A.nscr >> 24) & 0xff;
+        if (mode == 1 && max_len <= 256 && max_bins <= 127) {
+            Y.lz_hash = 256;
+            Y.npow2 = 256;                                   // sort path of dimensions 7, 8: <= 256 windows
+            Y.hist_cap = 896;                                // 1792 bytes of packed 16-bit counters
+            size_t o = 0;
+            Y.off_codes = (int)o; o += need_perm ? (size_t)1792 : 0;     // 870 packed 16-bit bins (dimensions 3..6), or 256 sort keys
+            Y.off_trie = (int)o;  o += (size_t)Y.lz_lanes * Y.lz_hash * 2;
+            Y.off_sym = (int)o;   o += (size_t)Y.lz_lanes * A.npad;
+            o = (o + 15) & ~(size_t)15;
+            Y.off_xs = (int)o;    o += (size_t)A.npad * 4;
+            const size_t per = (o + 15) & ~(size_t)15;
+            A.bytes_per_warp = (int)per;
+            Geometry G;
+            G.wpc = 4; G.smem = per * 4; G.gscratch = nullptr;
+            const int64_t ctas = (A.R.n_series + 3) / 4;
+            const int64_t cap = (int64_t)sm_count * grid_waves(4096);
+            G.grid = (int)std::max<int64_t>(1, std::min(ctas, cap));
+            A.gscratch = nullptr;
+            cudaError_t e = cudaFuncSetAttribute(k_seq_small<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+            if (e != cudaSuccess) return e;
+            k_seq_small<4, false><<<G.grid, 4 * 32, G.smem, st>>>(A, Y);
+            return cudaGetLastError();
+        }
+    }
     size_t off = 0;
     Y.off_codes = (int)off; off += need_perm ? (size_t)Y.npow2 * 4 : 0;
     Y.off_trie = (int)off;  off += (size_t)Y.lz_lanes * Y.lz_stride * 2;

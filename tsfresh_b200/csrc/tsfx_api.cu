@@ -327,6 +327,12 @@ static int group_of(int calc) {
 
 extern "C" int tsfx_version(void) { return TSFX_VERSION; }
 
+extern "C" int tsfx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 extern "C" const char* tsfx_last_error(const tsfx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int tsfx_ctx_create(int device, void* cuda_stream, tsfx_ctx** out) {
@@ -723,7 +729,7 @@ static int run_groups(tsfx_ctx* ctx, const tsfx_plan* P, const SeriesRef& R, int
                 SeqArgs A;
                 A.R = R; A.gscratch = gs_base; A.gscratch_bytes = slice; A.descs = P->dev[g]; A.nd = (int)P->host[g].size(); A.out = d_out; A.ncols = g_ncols;
                 A.nscr = (P->max_lz_bins > 0 ? 1 : 0) | (P->max_perm_dim > 0 ? 2 : 0) | (P->max_cwt_peaks_n << 8) |
-                         (std::min(P->n_lz, 255) << 16);
+                         (std::min(P->n_lz, 255) << 16) | (std::min(P->max_lz_bins, 255) << 24);
                 e = launch_seq(A, max_len, gs, ctx->sm_count);
                 break;
             }

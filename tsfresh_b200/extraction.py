@@ -11,8 +11,10 @@ Differences that are part of the contract (BASELINE.json north_star):
     float32-representable inputs;
   * there is no CPU fallback: a calculator or parameter without a GPU implementation raises
     NotImplementedError, a missing library or device raises RuntimeError;
-  * n_jobs / chunksize / distributor / profile* are accepted for signature compatibility; work always
-    runs on this process's CUDA device (one process per GPU, see tsfresh_b200.distributed).
+  * n_jobs is the number of GPUs this process may drive (the reference: worker processes, extraction.py:262-283): a
+    large frame whose rows arrive ordered by (id, sort) is cut at id boundaries and every GPU fills its rows of ONE
+    pinned result matrix; `device=` or a torchrun LOCAL_RANK pins the call to one GPU (one process per GPU, see
+    tsfresh_b200.distributed).  chunksize / profile* are accepted for signature compatibility.
 """
 import threading
 import warnings
@@ -171,6 +173,65 @@ def _encode_ids(id_series_list):
     return codes, uniq
 
 
+def _gpus_for(n_jobs, device):
+    """n_jobs -> devices one process drives: an explicit `device` or a torchrun-style LOCAL_RANK pins the
+    call to that GPU (one process per GPU); otherwise min(n_jobs, visible GPUs), at least one (n_jobs = 0, the
+    reference's "no parallelisation", is one GPU)."""
+    import os
+    if device is not None:
+        return [int(device)]
+    if "LOCAL_RANK" in os.environ:
+        return [int(os.environ["LOCAL_RANK"])]
+    have = max(1, _lib.device_count())
+    return list(range(max(1, min(int(n_jobs) if n_jobs else 1, have))))
+
+
+def _extract_long_multi(devices, plan, id_codes, sort_keys, v32):
+    """One frame over several GPUs of this process (n_jobs > 1): rows ordered by (id, sort key) are cut at id boundaries
+    into one contiguous shard per device; every device runs the pipelined long path on its shard from its own thread and
+    writes its rows straight into ONE pinned result matrix (no gather, no concatenation: the frame leaves the call as the
+    DataFrame's block).  Returns None when the rows are not in that order (the caller falls back to one GPU, which
+    sorts on the device)."""
+    n = len(id_codes)
+    G = len(devices)
+    cuts = [0]
+    for g in range(1, G):
+        r = max(cuts[-1], (n * g) // G)
+        while 0 < r < n and id_codes[r] == id_codes[r - 1]:
+            r += 1
+        cuts.append(r)
+    cuts.append(n)
+    shards = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    if len(shards) < 2:
+        return None
+    for (a, b), (c, d) in zip(shards[:-1], shards[1:]):            # shard boundaries must separate ascending ids
+        if not id_codes[b - 1] < id_codes[c]:
+            return None
+
+    def count(ab):
+        a, b = ab
+        return 1 + int(np.count_nonzero(id_codes[a + 1:b] != id_codes[a:b - 1]))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(shards)) as pool:
+        counts = list(pool.map(count, shards))                      # series per shard IF the ids inside it ascend
+        total = int(sum(counts))
+        ctx0 = get_context(devices[0])
+        out = ctx0.pinned_array((total, plan.n_cols), np.float64)
+        uid = ctx0.pinned_array((total,), np.int64)
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+        def run(k):
+            a, b = shards[k]
+            dp = _device_plan(get_context(devices[k]), plan)
+            sk = None if sort_keys is None else sort_keys[a:b]
+            got = dp.extract_long_into(id_codes[a:b], sk, v32[a:b], uid[offs[k]:offs[k + 1]], out[offs[k]:offs[k + 1]])
+            return got == counts[k]
+        ok = list(pool.map(run, range(len(shards))))
+    if not all(ok) or not bool(np.all(uid[1:] > uid[:-1])):          # some shard was not in (id, sort) order after all
+        return None
+    return uid, out
+
+
 def do_extraction_on_chunks(chunks, default_fc_parameters, kind_to_fc_parameters=None, show_warnings=True, device=None):
     """Batched form of the reference's per-series function (extraction.py:308-386): `chunks` is an iterable of
     (sample_id, kind, data) with `data` a pandas.Series or 1-d array already ordered in time; every chunk of one kind
@@ -307,7 +368,8 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
             raise ValueError("the passed distributor is not an DistributorBaseClass object")
 
     frames, id_dtype = _frames(timeseries_container, column_id, column_kind, column_value, column_sort)
-    ctx = get_context(device)
+    gpus = _gpus_for(n_jobs, device)
+    ctx = get_context(gpus[0])
     # impute_function=tsfresh_b200.impute: the feature matrix is imputed on the device before it is copied back
     from . import dataframe_functions as _dff
     device_impute = impute_function is _dff.impute
@@ -367,7 +429,13 @@ def extract_features(timeseries_container, default_fc_parameters=None, kind_to_f
         # linear_trend_timewise regresses on the rows' DatetimeIndex (feature_calculators.py:2296-2299)
         times = values.index.as_unit("ns").asi8 if plan.needs_times else None
         try:
-            uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags, times=times)
+            multi = None
+            if len(gpus) > 1 and times is None and not extract_flags and len(id_codes) >= (1 << 20):
+                multi = _extract_long_multi(gpus, plan, id_codes, _sort_keys(sort_col), v32)
+            if multi is not None:
+                uid, mat = multi
+            else:
+                uid, mat = dp.extract_long(id_codes, _sort_keys(sort_col), v32, flags=extract_flags, times=times)
         except ValueError as e:
             if "contains NaN" in str(e):          # TSFX_E_NAN: the check of data.py:148-167, done on the device
                 raise ValueError("Column must not contain NaN values: {}".format(value_name)) from None
