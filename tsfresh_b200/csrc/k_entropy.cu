@@ -431,20 +431,31 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
                 }
             }
             gsync<G>();
-            if (gw == 0) {              // inclusive scan of the histograms by one warp: lane l owns a contiguous run of ranks
-                const int run = (n + 31) >> 5;
-                const int b0 = lane * run;
+            {   // inclusive scan of the histograms by the whole group: thread t owns a contiguous run of ranks, warp scans by
+                // shuffle, warp totals through shared memory (with one warp per series the last step disappears)
+                const int run = (n + NTHR - 1) / NTHR;
+                const int b0 = tid * run;
+                unsigned v[8];
+                unsigned tot = 0u;
                 if (run <= 8) {         // the run lives in registers: one dependent shared-memory round trip, not one per rank
-                    unsigned v[8];
-                    unsigned tot = 0u;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { const int r = b0 + k; v[k] = (k < run && r < n) ? cnt[r] : 0u; }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { tot += v[k]; v[k] = tot; }
-                    unsigned inc = tot;
+                } else {
+                    for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
+                }
+                unsigned inc = tot;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned w = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += w; }
-                    const unsigned off = inc - tot;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned w = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += w; }
+                unsigned off = inc - tot;
+                if (G > 1) {
+                    unsigned* wtot = reinterpret_cast<unsigned*>(red);
+                    if (lane == 31) wtot[gw] = inc;
+                    __syncthreads();
+                    for (int w = 0; w < gw; ++w) off += wtot[w];
+                }
+                if (run <= 8) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int r = b0 + k;
@@ -455,12 +466,7 @@ __global__ void __launch_bounds__(G * SPC * 32, (G == 1 ? 4 : (G == 4 ? 4 : 1)))
                         }
                     }
                 } else {
-                    unsigned tot = 0u;
-                    for (int k = 0; k < run; ++k) { const int r = b0 + k; if (r < n) tot += cnt[r]; }
-                    unsigned inc = tot;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned w = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += w; }
-                    unsigned acc = inc - tot;
+                    unsigned acc = off;
                     for (int k = 0; k < run; ++k) {
                         const int r = b0 + k;
                         if (r < n) {
