@@ -301,14 +301,14 @@ class Bench:
         return self.torch.randn(shape, generator=gen, device=self.dev, dtype=self.torch.float32)
 
 
-def sharded_pass(B, name, values, S, L, steps, warmup, csr=None, placement="auto"):
+def sharded_pass(B, name, values, S, L, steps, warmup, csr=None, placement="auto", rows_alloc=None):
     """One configuration, device-resident: every rank extracts its S series (dense [S, L] tensor, or a CSR
     (begin, length) over `values`) and the rows are placed on every rank (tsfresh_b200.distributed.GatheredMatrix).
     Returns (ms per step max over ranks, per-group ms of one extra timed pass over this rank's shard, launches/step, gm)."""
     from tsfresh_b200.distributed import GatheredMatrix, extract_csr_sharded_device, extract_dense_sharded_device
     torch = B.torch
     plan, dp = B.plan(name)
-    gm = GatheredMatrix(S, plan.n_cols, B.dev, mode=placement)
+    gm = GatheredMatrix(rows_alloc or S, plan.n_cols, B.dev, mode=placement)      # same shape on every rank
     gm.attach(B.ctx)
     blocks = [1]
 
@@ -506,8 +506,11 @@ def main():
         v5 = B.randn((P5, L5), 42 + 4)                       # every rank holds the (164 MB) parent buffer
         wb_d = torch.from_numpy(wb[lo5:hi5].copy()).to(B.dev)
         wl_d = torch.from_numpy(wl[lo5:hi5].copy()).to(B.dev)
+        mx = torch.tensor([n5], device=B.dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         ms5, g5, _, gm5 = sharded_pass(B, "comprehensive", v5.reshape(-1), n5, 256, ksteps, kwarm, csr=(wb_d, wl_d),
-                                       placement=args.placement)
+                                       placement=args.placement, rows_alloc=int(mx.item()))
         nt = torch.tensor([n5], device=B.dev, dtype=torch.int64)
         if world > 1:
             dist.all_reduce(nt)

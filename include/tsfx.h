@@ -248,7 +248,8 @@ void tsfx_host_free(tsfx_ctx* ctx, void* p);
  *   TSFX_PEER_STORE      the assemble kernel stores each finished row to every peer (P2P stores over NVLink)
  *   TSFX_PEER_MULTICAST  the assemble kernel stores each row once through `multicast_out`, the multicast mapping of the
  *                        matrix (NVSwitch replicates the store to all ranks, this one included)
- *   TSFX_PEER_AUTO       MULTICAST when multicast_out != 0, else COPY
+ *   TSFX_PEER_AUTO       COPY (the fastest on B200 / NVSwitch: 204 ms per step at 2 GPUs against 209 STORE, 218 MULTICAST --
+ *                        8-byte multicast stores do not fill NVLink packets; profiles/r2_notes.md)
  * tsfx_peer_flush makes the context's stream wait for the copies in flight; the caller then synchronises the ranks
  * (barrier) before reading its matrix.  n_peers = 0 switches the placement off. */
 #define TSFX_PEER_AUTO 0

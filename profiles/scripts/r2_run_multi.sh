@@ -14,7 +14,7 @@ NCCL_DEBUG=WARN timeout 900 $TR bench.py --gpus $N > gpurun_out/r2_bench_${N}gpu
 tail -c 600 gpurun_out/r2_bench_${N}gpu.err
 head -c 400 gpurun_out/r2_bench_${N}gpu.json
 Q="--no-configs --no-e2e --no-cpu-baseline --steps 4 --warmup 2"
-for mode in copy store nccl multicast; do
+for mode in ${MODES:-copy store nccl multicast}; do
   timeout 300 $TR bench.py --gpus $N $Q --placement $mode > gpurun_out/r2_place_${mode}_${N}gpu.json 2> gpurun_out/r2_place_${mode}_${N}gpu.err
   head -c 200 gpurun_out/r2_place_${mode}_${N}gpu.json; tail -c 300 gpurun_out/r2_place_${mode}_${N}gpu.err
 done

@@ -1412,7 +1412,7 @@ extern "C" int tsfx_set_peer_outputs(tsfx_ctx* ctx, const uint64_t* peer_out, in
     if (n_peers <= 0) return TSFX_OK;
     if (!peer_out || self_index < 0 || self_index >= n_peers || n_peers > 8 || mode < TSFX_PEER_AUTO || mode > TSFX_PEER_MULTICAST)
         return fail(ctx, TSFX_E_INVALID, "tsfx_set_peer_outputs: bad arguments (at most 8 ranks)");
-    if (mode == TSFX_PEER_AUTO) mode = multicast_out ? TSFX_PEER_MULTICAST : TSFX_PEER_COPY;
+    if (mode == TSFX_PEER_AUTO) mode = TSFX_PEER_COPY;      // measured on 2 x B200: copy engines 204 ms, P2P stores 209, multicast stores 218 per step
     if (mode == TSFX_PEER_MULTICAST && !multicast_out) return fail(ctx, TSFX_E_INVALID, "no multicast mapping was supplied");
     ctx->peer_out.assign(peer_out, peer_out + n_peers);
     ctx->peer_self = self_index;

@@ -156,7 +156,7 @@ class GatheredMatrix:
             return self.kind
         want = {"auto": _lib.PEER_AUTO, "copy": _lib.PEER_COPY, "store": _lib.PEER_STORE, "multicast": _lib.PEER_MULTICAST}[self.mode]
         if want == _lib.PEER_AUTO:
-            want = _lib.PEER_MULTICAST if self.mc_ptr else _lib.PEER_COPY
+            want = _lib.PEER_COPY
         return {_lib.PEER_COPY: "copy engines over NVLink", _lib.PEER_STORE: "P2P stores from the assemble kernel",
                 _lib.PEER_MULTICAST: "multicast stores from the assemble kernel (NVSwitch)"}[want]
 
@@ -203,12 +203,14 @@ def extract_dense_sharded_device(dp, values, gm, stream=None, ctx_on_current_str
     S, L = values.shape
     stream = stream or torch.cuda.current_stream(values.device)
     nb = gm.n_blocks if gm.world > 1 else 1
-    bs = (S + nb - 1) // nb
+    span = gm.rows if gm.world > 1 else S      # every rank cuts the SAME row blocks (a short last shard is padded by the caller)
+    bs = (span + nb - 1) // nb
     for b in range(nb):
-        lo, hi = b * bs, min(S, (b + 1) * bs)
+        lo, hi = b * bs, min(span, (b + 1) * bs)
         if lo >= hi:
             break
-        dp.extract_dense_device(values[lo:hi].data_ptr(), hi - lo, L, gm.local_ptr(lo))
+        if lo < S:
+            dp.extract_dense_device(values[lo:min(hi, S)].data_ptr(), min(hi, S) - lo, L, gm.local_ptr(lo))
         if gm.kind == "nccl" and not ctx_on_current_stream:
             dp.ctx.sync()                  # the library ran on its own stream: order the exchange after it
         gm.block_done(lo, hi, stream)
@@ -221,13 +223,16 @@ def extract_csr_sharded_device(dp, values, begin, length, gm, stream=None, ctx_o
     S = int(begin.shape[0])
     stream = stream or torch.cuda.current_stream(values.device)
     nb = gm.n_blocks if gm.world > 1 else 1
-    bs = (S + nb - 1) // nb
+    span = gm.rows if gm.world > 1 else S
+    bs = (span + nb - 1) // nb
     for b in range(nb):
-        lo, hi = b * bs, min(S, (b + 1) * bs)
+        lo, hi = b * bs, min(span, (b + 1) * bs)
         if lo >= hi:
             break
-        dp.extract_csr_device(values.data_ptr(), values.numel(), begin[lo:hi].data_ptr(), length[lo:hi].data_ptr(), hi - lo,
-                              gm.local_ptr(lo), max_len=max_len)
+        if lo < S:
+            h = min(hi, S)
+            dp.extract_csr_device(values.data_ptr(), values.numel(), begin[lo:h].data_ptr(), length[lo:h].data_ptr(), h - lo,
+                                  gm.local_ptr(lo), max_len=max_len)
         if gm.kind == "nccl" and not ctx_on_current_stream:
             dp.ctx.sync()                  # the library ran on its own stream: order the exchange after it
         gm.block_done(lo, hi, stream)
