@@ -111,7 +111,7 @@ class GatheredMatrix:
         gm.finish(ctx)                                            # all ranks' rows are in gm.full after this
     """
 
-    def __init__(self, rows_per_rank, n_cols, device, group=None, mode="auto", n_blocks=8):
+    def __init__(self, rows_per_rank, n_cols, device, group=None, mode="auto", n_blocks=7):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -142,6 +142,22 @@ class GatheredMatrix:
             self.kind = "nccl" if self.world > 1 else "local"
         if self.kind == "nccl" and device.type == "cuda":
             self._comm = torch.cuda.Stream(device=device)
+
+    def block_bounds(self, span):
+        """Row blocks of one pass over `span` rows.  The placement of block b overlaps the kernels of block b + 1, so only
+        the LAST block's transfer is exposed: the blocks shrink geometrically towards the end (1/4, 1/4, 1/4, 1/8, 1/16,
+        1/32, 1/32 of the rows for the default of 7) -- big blocks keep the kernels' grids full, the exposed tail is 1/32
+        of the matrix instead of 1/8."""
+        if self.world <= 1 or self.n_blocks <= 1 or span < 64 * self.n_blocks:
+            return [0, span]
+        nb = self.n_blocks
+        fr = [0.25, 0.5, 0.75]
+        rest, x = nb - 3, 0.75
+        for k in range(rest - 1):
+            x += 0.25 / (2 ** (k + 1))
+            fr.append(x)
+        cuts = sorted(set([0] + [int(span * f) for f in fr] + [span]))
+        return cuts
 
     @property
     def local(self):
@@ -202,13 +218,10 @@ def extract_dense_sharded_device(dp, values, gm, stream=None, ctx_on_current_str
     b + 1) and leaves this rank's rows everywhere (gm)."""
     S, L = values.shape
     stream = stream or torch.cuda.current_stream(values.device)
-    nb = gm.n_blocks if gm.world > 1 else 1
     span = gm.rows if gm.world > 1 else S      # every rank cuts the SAME row blocks (a short last shard is padded by the caller)
-    bs = (span + nb - 1) // nb
-    for b in range(nb):
-        lo, hi = b * bs, min(span, (b + 1) * bs)
-        if lo >= hi:
-            break
+    cuts = gm.block_bounds(span)
+    nb = len(cuts) - 1
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
         if lo < S:
             dp.extract_dense_device(values[lo:min(hi, S)].data_ptr(), min(hi, S) - lo, L, gm.local_ptr(lo))
         if gm.kind == "nccl" and not ctx_on_current_stream:
@@ -222,13 +235,10 @@ def extract_csr_sharded_device(dp, values, begin, length, gm, stream=None, ctx_o
     int64 / int32 CUDA tensors over the shared `values` buffer."""
     S = int(begin.shape[0])
     stream = stream or torch.cuda.current_stream(values.device)
-    nb = gm.n_blocks if gm.world > 1 else 1
     span = gm.rows if gm.world > 1 else S
-    bs = (span + nb - 1) // nb
-    for b in range(nb):
-        lo, hi = b * bs, min(span, (b + 1) * bs)
-        if lo >= hi:
-            break
+    cuts = gm.block_bounds(span)
+    nb = len(cuts) - 1
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
         if lo < S:
             h = min(hi, S)
             dp.extract_csr_device(values.data_ptr(), values.numel(), begin[lo:h].data_ptr(), length[lo:h].data_ptr(), h - lo,
