@@ -26,4 +26,15 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_b
     python bench.py --steps 1 --warmup 0 --series 200000 $Q > $O/ncu_final.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_moments -c 1 -f -o $O/r2_final_moments \
     python bench.py --steps 1 --warmup 0 --settings minimal $Q >> $O/ncu_final.log 2>&1
+# text summaries on the box (the reports themselves exceed the 64 MiB that travel back)
+python profiles/scripts/ncu_summary.py $O/r2_final_kernels.ncu-rep "k_" 14 > $O/ncu_r2_summary.txt 2>&1
+python profiles/scripts/ncu_summary.py $O/r2_final_moments.ncu-rep "k_moments" 12 >> $O/ncu_r2_summary.txt 2>&1
+ncu -i $O/r2_final_kernels.ncu-rep --page raw --csv --kernel-name regex:k_basic 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin)); h=rows[0]; v=rows[2]
+for n,x in zip(h,v):
+    if 'dmma' in n.lower() or 'pipe_tensor_cycles' in n: print(n, x)
+" > $O/ncu_r2_basic_tensor_pipe.txt 2>&1
+rm -f $O/*.ncu-rep
+du -sh $O
 head -c 500 $O/bench_r2.json
