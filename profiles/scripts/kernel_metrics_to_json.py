@@ -16,7 +16,7 @@ dst = sys.argv[2] if len(sys.argv) > 2 else src.replace("kernel_metrics", "traff
 rows = list(csv.reader(l for l in open(src) if not l.startswith("==")))
 ix = {h: i for i, h in enumerate(rows[0])}
 per = {}
-ALIAS = {"k_entropy_rank": "k_entropy", "k_moments_dense": "k_moments"}      # one bench group per kernel family
+ALIAS = {"k_entropy_rank": "k_entropy", "k_moments_dense": "k_moments", "k_seq_small": "k_seq"}      # one bench group per kernel family
 for r in rows[1:]:
     if len(r) < len(rows[0]):
         continue

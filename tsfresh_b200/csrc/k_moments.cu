@@ -246,18 +246,21 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_moments_dense(MomentsArgs A) {
         const int64_t s = s0 + slot;
         const bool live = s < A.R.n_series;
         fetch(nxt, s + stride);                          // in flight while this series is reduced
-        double sm = 0.0, sq = 0.0;
+        // four independent accumulators per sum: a single fma chain over the lane's 32 samples would be 32 dependent
+        // FP64 operations (the kernel was bound by exactly that: stall "wait" 2.9 per issued instruction)
+        double sm4[4] = {0.0, 0.0, 0.0, 0.0}, sq4[4] = {0.0, 0.0, 0.0, 0.0};
         float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
         for (int k = 0; k < REG; ++k) {
             if (sub + k * SUB < n4) {
                 const double a = (double)cur[k].x, bb = (double)cur[k].y, cc = (double)cur[k].z, dd = (double)cur[k].w;
-                sm += (a + bb) + (cc + dd);
-                sq = fma(a, a, sq); sq = fma(bb, bb, sq); sq = fma(cc, cc, sq); sq = fma(dd, dd, sq);
+                sm4[0] += a; sm4[1] += bb; sm4[2] += cc; sm4[3] += dd;
+                sq4[0] = fma(a, a, sq4[0]); sq4[1] = fma(bb, bb, sq4[1]); sq4[2] = fma(cc, cc, sq4[2]); sq4[3] = fma(dd, dd, sq4[3]);
                 lo = fminf(fminf(lo, cur[k].x), fminf(cur[k].y, fminf(cur[k].z, cur[k].w)));
                 hi = fmaxf(fmaxf(hi, cur[k].x), fmaxf(cur[k].y, fmaxf(cur[k].z, cur[k].w)));
             }
         }
+        const double sm = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]), sq = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
         MomStats S;
         S.n = (double)n;
         S.sum = gsum<SUB>(sm);
@@ -266,19 +269,20 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_moments_dense(MomentsArgs A) {
         S.vmax = (double)gmaxf<SUB>(hi);
         S.mean = S.sum / S.n;
         const double mu = S.mean;
-        double a2 = 0.0, a3 = 0.0, a4 = 0.0;
+        double b2[4] = {0.0, 0.0, 0.0, 0.0}, b3[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < REG; ++k) {
             if (sub + k * SUB < n4) {
                 const double d0 = (double)cur[k].x - mu, d1 = (double)cur[k].y - mu, d2 = (double)cur[k].z - mu, d3 = (double)cur[k].w - mu;
                 const double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2, q3 = d3 * d3;
-                a2 += (q0 + q1) + (q2 + q3);
+                b2[0] += q0; b2[1] += q1; b2[2] += q2; b2[3] += q3;
                 if (A.need_high) {
-                    a3 = fma(q0, d0, a3); a3 = fma(q1, d1, a3); a3 = fma(q2, d2, a3); a3 = fma(q3, d3, a3);
-                    a4 = fma(q0, q0, a4); a4 = fma(q1, q1, a4); a4 = fma(q2, q2, a4); a4 = fma(q3, q3, a4);
+                    b3[0] = fma(q0, d0, b3[0]); b3[1] = fma(q1, d1, b3[1]); b3[2] = fma(q2, d2, b3[2]); b3[3] = fma(q3, d3, b3[3]);
+                    b4[0] = fma(q0, q0, b4[0]); b4[1] = fma(q1, q1, b4[1]); b4[2] = fma(q2, q2, b4[2]); b4[3] = fma(q3, q3, b4[3]);
                 }
             }
         }
+        const double a2 = (b2[0] + b2[1]) + (b2[2] + b2[3]), a3 = (b3[0] + b3[1]) + (b3[2] + b3[3]), a4 = (b4[0] + b4[1]) + (b4[2] + b4[3]);
         S.m2 = gsum<SUB>(a2);
         S.m3 = A.need_high ? gsum<SUB>(a3) : 0.0;
         S.m4 = A.need_high ? gsum<SUB>(a4) : 0.0;
