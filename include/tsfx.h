@@ -303,6 +303,17 @@ int tsfx_impute(tsfx_ctx* ctx, double* matrix, int64_t n_rows, int32_t n_cols, i
 int tsfx_select_classification(tsfx_ctx* ctx, const double* X, int64_t n_rows, int32_t n_cols, const int32_t* y_codes,
                                int32_t n_classes, double* out, uint32_t flags);
 
+/* Same for REGRESSION targets (relevance.py:282-296; significance_tests.py:135-188): y is the float64 target of every row.
+ * out: n_cols x TSFX_SEL_NSTAT doubles + 4 trailing doubles { sum t(t-1)/2, sum t(t-1)(t-2), sum t(t-1)(2t+5) over the
+ * tie groups of y, n_rows }:
+ *     0: feature type   1: n_rows
+ *     real feature (Kendall's tau, scipy.stats.kendalltau method="asymptotic"):  2: discordant pairs   3..5: the three tie
+ *                      sums of the feature   6: joint ties sum c(c-1)/2 of (x, y)
+ *     binary feature (two-sample KS of the target, scipy.stats.ks_2samp):  2: KS statistic   3: rows with the larger value
+ *                      4: rows with the smaller value */
+int tsfx_select_regression(tsfx_ctx* ctx, const double* X, int64_t n_rows, int32_t n_cols, const double* y, double* out,
+                           uint32_t flags);
+
 /* Per-kernel-group device time (ms) of the last extract call made with TSFX_FLAG_TIMING.
  * names_out[i] points at a static string.  Returns the number of groups written (<= cap). */
 int tsfx_get_timings(tsfx_ctx* ctx, float* ms_out, const char** names_out, int32_t cap);

@@ -41,12 +41,17 @@ def main():
         out[tag + "_y2"] = y2
         out[tag + "_y3"] = y3
         out["columns"] = np.array(list(X.columns))
+        yr = (X["signal_1"].to_numpy() * 0.5 + 0.2 * X["binary_rel"].to_numpy() + rng.standard_normal(n))      # regression target
+        yt = np.round(yr * 2) / 2                                                                               # ... with ties
+        out[tag + "_yr"] = yr
+        out[tag + "_yt"] = yt
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            for ytag, y, kw in (("y2", y2, {}), ("y2smir", y2, {"test_for_binary_target_real_feature": "smir"}),
+            for ytag, y, kw in (("yr", yr, {}), ("yt", yt, {"hypotheses_independent": True}), ("y2", y2, {}), ("y2smir", y2, {"test_for_binary_target_real_feature": "smir"}),
                                 ("y2indep", y2, {"hypotheses_independent": True, "fdr_level": 0.2}),
                                 ("y3", y3, {"multiclass": True, "n_significant": 2})):
-                t = calculate_relevance_table(X, pd.Series(y, index=X.index), ml_task="classification", n_jobs=0, **kw)
+                task = "regression" if ytag in ("yr", "yt") else "classification"
+                t = calculate_relevance_table(X, pd.Series(y, index=X.index), ml_task=task, n_jobs=0, **kw)
                 key = "%s_%s" % (tag, ytag)
                 out[key + "_index"] = np.array(list(t.index))
                 out[key + "_columns"] = np.array(list(t.columns))

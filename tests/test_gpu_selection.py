@@ -1,6 +1,7 @@
 """Feature selection on the GPU (tsfresh_b200.feature_selection, csrc/tsfx_select.cu) against golden relevance tables of the
 UNMODIFIED reference (tests/golden/selection.npz from oracle/make_golden_selection.py: relevance.py:31-322 with scipy's
-mannwhitneyu / ks_2samp / fisher_exact) -- binary and multiclass targets, real / tied / binary / constant features."""
+mannwhitneyu / ks_2samp / fisher_exact / kendalltau) -- binary, multiclass and regression targets (with and without ties),
+real / tied / binary / constant features."""
 import os
 import warnings
 
@@ -13,7 +14,7 @@ from tsfresh_b200.feature_selection import calculate_relevance_table, select_fea
 pytestmark = pytest.mark.gpu
 Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "selection.npz"), allow_pickle=True)
 
-CASES = {"y2": ("y2", {}), "y2smir": ("y2", {"test_for_binary_target_real_feature": "smir"}),
+CASES = {"yr": ("yr", {}), "yt": ("yt", {"hypotheses_independent": True}), "y2": ("y2", {}), "y2smir": ("y2", {"test_for_binary_target_real_feature": "smir"}),
          "y2indep": ("y2", {"hypotheses_independent": True, "fdr_level": 0.2}),
          "y3": ("y3", {"multiclass": True, "n_significant": 2})}
 
@@ -26,7 +27,7 @@ def test_relevance_table_matches_the_reference(size, case):
     y = pd.Series(Z["%s_%s" % (size, ycol)], index=X.index)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        t = calculate_relevance_table(X, y, ml_task="classification", **kw)
+        t = calculate_relevance_table(X, y, ml_task="regression" if case in ("yr", "yt") else "classification", **kw)
     key = "%s_%s" % (size, case)
     assert list(t.columns) == list(Z[key + "_columns"])
     assert sorted(t.index) == sorted(Z[key + "_index"])
@@ -54,8 +55,10 @@ def test_select_features_and_errors():
     rel = pd.Series(Z["large_y2_col_relevant"], index=Z["large_y2_index"]).astype(bool)
     assert sorted(sel.columns) == sorted(rel.index[rel.to_numpy()])
     assert "constant" not in sel.columns and len(sel) == len(X)
-    with pytest.raises(NotImplementedError):
-        calculate_relevance_table(X, pd.Series(np.random.default_rng(0).standard_normal(len(X))), ml_task="regression")
+    with pytest.raises(ValueError, match="NaN"):
+        yn = np.random.default_rng(0).standard_normal(len(X))
+        yn[3] = np.nan
+        calculate_relevance_table(X, pd.Series(yn), ml_task="regression")
     Xn = X.copy()
     Xn.iloc[5, 3] = np.nan
     with pytest.raises(ValueError, match="NaN"):

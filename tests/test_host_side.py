@@ -307,3 +307,33 @@ def test_feature_selection_pvalues_match_scipy():
     assert list(benjamini_reject([0.03, 0.001, 0.5, 0.02], 0.05, True)) == [True, True, False, True]
     # Benjamini-Yekutieli divides the thresholds by 1 + 1/2 + 1/3 + 1/4
     assert list(benjamini_reject([0.03, 0.001, 0.5, 0.02], 0.05, False)) == [False, True, False, False]
+
+
+def test_kendall_pvalue_from_sufficient_statistics_matches_scipy():
+    """the statistics tsfx_select_regression returns (discordant pairs, tie sums, joint ties) give scipy's asymptotic
+    Kendall p-value (significance_tests.py:170-188); the statistics are formed here by brute force"""
+    from scipy import stats
+    from tsfresh_b200.feature_selection import kendall_pvalue
+    rng = np.random.default_rng(5)
+
+    def tie_sums(v):
+        _, t = np.unique(v, return_counts=True)
+        t = t.astype(np.float64)
+        return (t * (t - 1) // 2).sum(), (t * (t - 1) * (t - 2)).sum(), (t * (t - 1) * (2 * t + 5)).sum()
+
+    for trial in range(60):
+        n = int(rng.integers(3, 80))
+        if trial % 3 == 0:
+            x, y = rng.standard_normal(n), rng.standard_normal(n)
+        elif trial % 3 == 1:
+            x, y = rng.integers(0, 5, n).astype(float), rng.standard_normal(n)
+        else:
+            x, y = rng.integers(0, 4, n).astype(float), rng.integers(0, 3, n).astype(float)
+        dx, dy = x[:, None] - x[None, :], y[:, None] - y[None, :]
+        dis = int(np.sum((dx < 0) & (dy > 0)))
+        _, joint = np.unique(np.stack([x, y], axis=1), axis=0, return_counts=True)
+        ntie = int((joint * (joint - 1) // 2).sum())
+        xt, yt = tie_sums(x), tie_sums(y)
+        got = kendall_pvalue(n, dis, int(xt[0]), xt[1], xt[2], ntie, int(yt[0]), yt[1], yt[2])
+        want = stats.kendalltau(x, y, method="asymptotic").pvalue
+        assert (np.isnan(got) and np.isnan(want)) or abs(got - want) < 1e-12

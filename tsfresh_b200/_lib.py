@@ -29,7 +29,7 @@ EXPORTS = ["tsfx_ctx_create", "tsfx_ctx_destroy", "tsfx_last_error", "tsfx_sync"
            "tsfx_plan_create", "tsfx_plan_destroy", "tsfx_extract_csr", "tsfx_extract_dense",
            "tsfx_extract_long", "tsfx_build_csr", "tsfx_roll_windows", "tsfx_get_timings",
            "tsfx_last_launch_count", "tsfx_impute", "tsfx_extract_long_alloc", "tsfx_host_alloc", "tsfx_host_free",
-           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification", "tsfx_extract_long_kinds", "tsfx_device_count"]
+           "tsfx_set_peer_outputs", "tsfx_peer_flush", "tsfx_set_max_len_hint", "tsfx_set_row_times", "tsfx_select_classification", "tsfx_extract_long_kinds", "tsfx_device_count", "tsfx_select_regression"]
 
 
 def load():
@@ -72,6 +72,7 @@ def load():
         lib.tsfx_set_max_len_hint.argtypes = [vp, i32]
         lib.tsfx_set_row_times.argtypes = [vp, vp, i64, u32]
         lib.tsfx_select_classification.argtypes = [vp, vp, i64, i32, vp, i32, vp, u32]
+        lib.tsfx_select_regression.argtypes = [vp, vp, i64, i32, vp, vp, u32]
         lib.tsfx_extract_long_kinds.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                                 ctypes.POINTER(i64), u32]
         _lib = lib
@@ -186,6 +187,17 @@ class Context:
             rc = self.lib.tsfx_select_classification(self.h, _ptr(X), n, f, _ptr(y), int(n_classes), _ptr(out), 0)
             self.check(rc, "tsfx_select_classification")
         return out
+
+    def select_regression(self, X, y):
+        """tsfx_select_regression on host arrays: returns ([n_cols, 8] statistics, (ytie, y0, y1, n))"""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n, f = X.shape
+        out = np.zeros(f * 8 + 4, dtype=np.float64)
+        with self.lock:
+            rc = self.lib.tsfx_select_regression(self.h, _ptr(X), n, f, _ptr(y), _ptr(out), 0)
+            self.check(rc, "tsfx_select_regression")
+        return out[:f * 8].reshape(f, 8), out[f * 8:]
 
     def set_row_times(self, times_ns):
         """timestamps (int64 ns) of the rows of the NEXT extract call's values (linear_trend_timewise)"""

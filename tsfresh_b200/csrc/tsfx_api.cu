@@ -1400,6 +1400,34 @@ extern "C" int tsfx_select_classification(tsfx_ctx* ctx, const double* X, int64_
     return TSFX_OK;
 }
 
+extern "C" int tsfx_select_regression(tsfx_ctx* ctx, const double* X, int64_t n_rows, int32_t n_cols, const double* y, double* out,
+                                      uint32_t flags) {
+    if (!ctx) return TSFX_E_INVALID;
+    if (n_rows < 1 || n_cols < 0 || !y || !out || (n_cols > 0 && !X))
+        return fail(ctx, TSFX_E_INVALID, "tsfx_select_regression: bad arguments");
+    if (n_cols == 0) return TSFX_OK;
+    CK(cudaSetDevice(ctx->device));
+    const double* d_X = X;
+    if (!(flags & TSFX_FLAG_DEVICE_PTRS)) {
+        CK(ctx->sel_x.reserve((size_t)n_rows * n_cols * 8));
+        CK(ctx->stager.h2d(ctx->sel_x.p, X, (size_t)n_rows * n_cols * 8, ctx->stream));
+        d_X = (const double*)ctx->sel_x.p;
+    }
+    CK(ctx->sel_y.reserve((size_t)n_rows * 8));
+    CK(ctx->stager.h2d(ctx->sel_y.p, y, (size_t)n_rows * 8, ctx->stream));
+    const size_t ob = ((size_t)n_cols * TSFX_SEL_NSTAT + 4) * sizeof(double);
+    CK(ctx->sel_out.reserve(ob));
+    std::string msg;
+    int has_nan = 0;
+    int rc = select_regression_stats(ctx->sel, d_X, n_rows, n_cols, (const double*)ctx->sel_y.p, (double*)ctx->sel_out.p, &has_nan,
+                                     ctx->stream, &msg);
+    if (rc) return fail(ctx, rc, msg);
+    CK(cudaMemcpyAsync(out, ctx->sel_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (has_nan) return fail(ctx, TSFX_E_NAN, "the feature matrix or the target contains NaN");
+    return TSFX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ multi-GPU placement
 extern "C" int tsfx_set_peer_outputs(tsfx_ctx* ctx, const uint64_t* peer_out, int32_t n_peers, int32_t self_index,
                                      uint64_t multicast_out, int32_t mode) {

@@ -15,8 +15,12 @@ one pass over the sorted column (tsfx_select_classification, csrc/tsfx_select.cu
 What is left for the host is O(n_features): the p-value of each statistic (the closed forms scipy itself evaluates: normal
 tail with continuity and tie correction / exact U distribution for tiny untied samples, hypergeometric tail, Kolmogorov
 distributions) and the Benjamini-Hochberg / Benjamini-Yekutieli step-up decision (statsmodels.stats.multitest.multipletests
-in the reference, relevance.py:347-351).  Regression targets (Kendall's tau, KS on the target) have no device path yet and
-raise NotImplementedError -- there is no CPU fallback.
+in the reference, relevance.py:347-351).
+
+REGRESSION targets (relevance.py:282-296) take tsfx_select_regression: real features need Kendall's tau -- the rows are
+brought into (x, rank(y)) order by two stable device sorts, the discordant pairs are the strict inversions of the rank
+sequence (bottom-up merge, one kernel per level), tie sums come from the runs; binary features need the two-sample KS of
+the target between their two groups (one pass over the y-sorted rows).
 """
 import math
 import warnings
@@ -99,6 +103,19 @@ def ks_2samp_pvalue(d, n1, n2):
     m, n = sorted([float(n1), float(n2)], reverse=True)
     en = m * n / (m + n)
     return float(np.clip(stats.distributions.kstwo.sf(d, np.round(en)), 0, 1))
+
+
+def kendall_pvalue(n, dis, xtie, x0, x1, ntie, ytie, y0, y1):
+    """scipy.stats.kendalltau(x, y, method="asymptotic").pvalue (tau-b) from its sufficient statistics: discordant pairs,
+    the tie sums sum t(t-1)/2, sum t(t-1)(t-2), sum t(t-1)(2t+5) of x and y and the joint ties (scipy _stats_py.py)."""
+    tot = n * (n - 1) // 2
+    if xtie == tot or ytie == tot:
+        return math.nan
+    con_minus_dis = tot - xtie - ytie + ntie - 2 * dis
+    m = n * (n - 1.0)
+    var = (m * (2 * n + 5) - x1 - y1) / 18 + (2 * xtie * ytie) / m + x0 * y0 / (9 * m * (n - 2))
+    z = con_minus_dis / math.sqrt(var)
+    return math.erfc(abs(z) / math.sqrt(2.0))
 
 
 def fisher_pvalue(n_y1_x1, n_y1_x0, n_y0_x1, n_y0_x0):
@@ -194,25 +211,30 @@ def calculate_relevance_table(X, y, ml_task="auto", multiclass=False, n_signific
         if len(y.unique()) <= 2:
             warnings.warn("Two or fewer classes, binary feature selection will be used (multiclass = False)")
             multiclass = False
-    if ml_task == "regression":
-        raise NotImplementedError("feature selection for regression targets (Kendall's tau / KS on the target, "
-                                  "significance_tests.py:135-188) has no GPU implementation yet; there is no CPU fallback")
 
     with warnings.catch_warnings():
         warnings.simplefilter("default" if show_warnings else "ignore")
         features = list(X.columns)
-        labels = list(y.unique())                        # order of appearance, as the reference's loop (relevance.py:248)
-        codes = pd.Categorical(y, categories=labels).codes.astype(np.int32)
         M = np.ascontiguousarray(X.to_numpy(dtype=np.float64))
         ctx = get_context(device)
         try:
-            stats = ctx.select_classification(M, codes, len(labels))      # [n_labels, n_features, 8]
+            if ml_task == "classification":
+                labels = list(y.unique())                # order of appearance, as the reference's loop (relevance.py:248)
+                codes = pd.Categorical(y, categories=labels).codes.astype(np.int32)
+                stats = ctx.select_classification(M, codes, len(labels))      # [n_labels, n_features, 8]
+                type_col = stats[0, :, 0]
+            else:
+                yv = np.ascontiguousarray(y.to_numpy(dtype=np.float64))
+                if np.isnan(yv).any():
+                    raise ValueError("Target y contains NaN values")
+                rstats, ytail = ctx.select_regression(M, yv)                  # [n_features, 8], (ytie, y0, y1, n)
+                type_col = rstats[:, 0]
         except ValueError as e:
-            if "NaN" in str(e):
+            if "NaN" in str(e) and "Target" not in str(e):
                 raise ValueError("Feature {} contains NaN values".format("matrix")) from None
             raise
         type_names = {0: "constant", 1: "binary", 2: "real"}
-        types = [type_names[int(t)] for t in stats[0, :, 0]]
+        types = [type_names[int(t)] for t in type_col]
         const = [i for i, t in enumerate(types) if t == "constant"]
         table_const = pd.DataFrame({"feature": [features[i] for i in const], "type": ["constant"] * len(const)},
                                    index=pd.Index([features[i] for i in const], name="feature"))
@@ -224,6 +246,24 @@ def calculate_relevance_table(X, y, ml_task="auto", multiclass=False, n_signific
         if len(table_const) == len(features):
             return table_const
 
+        if ml_task == "regression":
+            # relevance.py:282-296: Kendall's tau for real features, two-sample KS of the target for binary ones
+            n = int(ytail[3])
+            real = [i for i, t in enumerate(types) if t == "real"]
+            binary = [i for i, t in enumerate(types) if t == "binary"]
+            p = {}
+            for i in real:
+                s_ = rstats[i]
+                p[i] = kendall_pvalue(n, int(s_[2]), int(s_[3]), s_[4], s_[5], int(s_[6]), int(ytail[0]), ytail[1], ytail[2])
+            for i in binary:
+                s_ = rstats[i]
+                p[i] = ks_2samp_pvalue(s_[2], s_[3], s_[4])
+            idx = real + binary
+            relevance_table = pd.DataFrame({"feature": [features[i] for i in idx], "type": [types[i] for i in idx],
+                                            "p_value": [p[i] for i in idx]}, index=pd.Index([features[i] for i in idx], name="feature"))
+            relevance_table["relevant"] = benjamini_reject(relevance_table.p_value.to_numpy(), fdr_level, hypotheses_independent)
+            relevance_table = relevance_table.sort_values("p_value")
+            labels = []
         tables = []
         for k, label in enumerate(labels):
             tmp = _table_for_label(features, types, stats[k], test_for_binary_target_real_feature, fdr_level,
@@ -232,7 +272,9 @@ def calculate_relevance_table(X, y, ml_task="auto", multiclass=False, n_signific
                 tmp = tmp.reset_index(drop=True)
                 tmp.columns = tmp.columns.map(lambda x: (x + "_" + str(label) if x != "feature" and x != "type" else x))
             tables.append(tmp)
-        if multiclass:
+        if ml_task == "regression":
+            pass
+        elif multiclass:
             relevance_table = reduce(lambda left, right: pd.merge(left, right, on=["feature", "type"], how="outer"), tables)
             relevance_table["n_significant"] = relevance_table.filter(regex="^relevant_", axis=1).sum(axis=1)
             relevance_table["relevant"] = relevance_table["n_significant"] >= n_significant
