@@ -99,6 +99,7 @@ class Context:
         self.h = h
         self.device = int(device)
         self._plans = {}
+        self._alive = {"h": h}           # shared with the finalizers of pinned arrays: None once the context is destroyed
         # the context owns device scratch that every entry point reuses: calls on one context are serialised
         # (include/tsfx.h "Threading"); ctypes releases the GIL, so the lock is needed for multi-threaded callers
         self.lock = threading.RLock()
@@ -108,6 +109,7 @@ class Context:
             for p in list(self._plans.values()):
                 p.close()
             self._plans.clear()
+            self._alive["h"] = None      # pinned arrays still alive keep their memory (not returned to a destroyed pool)
             self.lib.tsfx_ctx_destroy(self.h)
             self.h = None
 
@@ -173,8 +175,12 @@ class Context:
         n = int(np.prod(shape)) * dtype.itemsize
         buf = (ctypes.c_char * max(n, 1)).from_address(p)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        lib, h = self.lib, self.h
-        weakref.finalize(buf, lambda lib=lib, h=h, p=p: lib.tsfx_host_free(h, ctypes.c_void_p(p)))
+        lib, alive = self.lib, self._alive
+
+        def give_back(lib=lib, alive=alive, p=p):
+            if alive["h"] is not None:
+                lib.tsfx_host_free(alive["h"], ctypes.c_void_p(p))
+        weakref.finalize(buf, give_back)
         return arr
 
     def select_classification(self, X, y_codes, n_classes):

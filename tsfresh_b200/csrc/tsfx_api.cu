@@ -106,9 +106,10 @@ struct HostPool {
         idle.clear();
     }
     void release_all() {
+        // blocks still handed out (a DataFrame may live on one) are deliberately NOT freed when the context goes away:
+        // they stay valid until the process exits
         trim();
         std::lock_guard<std::mutex> g(mu);
-        for (auto& kv : live) cudaFreeHost(kv.first);
         live.clear();
     }
 };
