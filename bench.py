@@ -2,17 +2,23 @@
 """bench.py -- series/sec of the feature-extraction hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--series S] [--len L]
-                    [--settings comprehensive|efficient|minimal]
+                    [--settings comprehensive|efficient|minimal] [--placement auto|copy|store|multicast|nccl]
 
 A "step" is one pass of the hot path (ComprehensiveFCParameters, 783 columns) over one batch of S synthetic
 series of length L per GPU (default 1 000 000 x 256 = BASELINE.json configs[2], the configuration the
 metric and the north-star target are quoted on).  Weak scaling: every rank owns S series (ids sharded
-contiguously, no data-path collective inside the kernels); with N > 1 the step ends with the north star's
-single all-gather of the [N*S x F] matrix, issued per row block on a side stream so it overlaps the kernels.
+contiguously, no data-path collective inside the kernels); with N > 1 every rank's finished row blocks are placed
+in every rank's copy of the [N*S x F] matrix (tsfresh_b200.distributed.GatheredMatrix: symmetric memory + copy
+engines over NVLink while the next block's kernels run; no collective kernel).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM, CUDA-event
 timed, max over ranks); `e2e` = the same pass through the C-ABI host entry point (tsfx_extract_dense with
-pinned HOST buffers: H2D of the values and D2H of the feature matrix inside the timed region).
+pinned HOST buffers: H2D of the values and D2H of the feature matrix inside the timed region); `e2e_long` = from a
+long (id, time, value) frame of 20 bytes per row (tsfx_extract_long_alloc, stage (a) included); `e2e_api` =
+tsfresh_b200.extract_features(pandas.DataFrame).  `configs` carries the other BASELINE configurations measured in the
+same run: config2 (Efficient 100 k x 256, N = 1), config4 (Comprehensive 1 M x 1024 in total, strong scaling),
+config5 (roll_time_series 10 k x 4096 -> 1.21 M window views, sharded by parent), minimal (the reduction-only
+kernel behind `roofline.minimal`).
 `--impl reference` times the CPU path (the oracle port of the reference, all host cores) instead.
 """
 import argparse

@@ -337,3 +337,58 @@ def test_kendall_pvalue_from_sufficient_statistics_matches_scipy():
         got = kendall_pvalue(n, dis, int(xt[0]), xt[1], xt[2], ntie, int(yt[0]), yt[1], yt[2])
         want = stats.kendalltau(x, y, method="asymptotic").pvalue
         assert (np.isnan(got) and np.isnan(want)) or abs(got - want) < 1e-12
+
+
+def _gm_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tsfresh_b200.distributed import GatheredMatrix
+        gm = GatheredMatrix(1000, 7, torch.device("cpu"), n_blocks=7)
+        assert gm.kind == "nccl" and gm.placement() == "nccl"          # no symmetric memory on the host: exchange of row blocks
+        gm.local[:] = torch.arange(1000 * 7, dtype=torch.float64).reshape(1000, 7) + 1e6 * rank
+        cuts = gm.block_bounds(gm.rows)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):                       # what extract_*_sharded_device does after every block
+            gm.block_done(lo, hi, None)
+        gm.finish(None)
+        want = torch.cat([torch.arange(7000, dtype=torch.float64).reshape(1000, 7) + 1e6 * r for r in range(world)])
+        ret[rank] = bool(torch.equal(gm.full, want)), cuts
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gathered_matrix_row_blocks_world_size_2_gloo():
+    """the product's result placement (tsfresh_b200.distributed.GatheredMatrix) without GPUs: geometric row blocks,
+    the same cuts on every rank, block-wise exchange -> every rank holds every rank's rows"""
+    import socket
+    import torch.multiprocessing as mp
+    from tsfresh_b200.distributed import GatheredMatrix
+    g = GatheredMatrix.__new__(GatheredMatrix)
+    g.world, g.n_blocks = 8, 7
+    cuts = g.block_bounds(1_000_000)
+    assert cuts == [0, 250000, 500000, 750000, 875000, 937500, 968750, 1000000]
+    assert g.block_bounds(100) == [0, 100]                            # tiny shards: one block
+    g.world = 1
+    assert g.block_bounds(1_000_000) == [0, 1_000_000]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gm_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0][0] and ret[1][0] and ret[0][1] == ret[1][1] and len(ret[0][1]) == 8
+
+
+def test_n_jobs_maps_to_gpus(monkeypatch):
+    from tsfresh_b200 import _lib, extraction
+    monkeypatch.setattr(_lib, "device_count", lambda: 8)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    assert extraction._gpus_for(64, None) == list(range(8))          # the reference's default n_jobs: every visible GPU
+    assert extraction._gpus_for(2, None) == [0, 1]
+    assert extraction._gpus_for(0, None) == [0] and extraction._gpus_for(1, None) == [0]
+    assert extraction._gpus_for(64, 5) == [5]                         # explicit device wins
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    assert extraction._gpus_for(64, None) == [3]                      # one process per GPU under torchrun

@@ -191,6 +191,11 @@ class GatheredMatrix:
         """rows [lo, hi) of the local shard are final on `stream` (nccl fallback: exchange them now, overlapped)"""
         if self.kind != "nccl":
             return
+        if self.device.type != "cuda":                 # gloo on the host (CPU tests): a plain blocking exchange
+            stage = torch.empty((self.world, hi - lo, self.n_cols), dtype=torch.float64)
+            dist.all_gather_into_tensor(stage.view(-1), self.local[lo:hi].reshape(-1).contiguous(), group=self.group)
+            self.full.view(self.world, self.rows, self.n_cols)[:, lo:hi].copy_(stage)
+            return
         ev = torch.cuda.Event()
         ev.record(stream)
         with torch.cuda.stream(self._comm):
