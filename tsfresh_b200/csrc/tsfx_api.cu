@@ -1171,13 +1171,11 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* const* plans, const
     KindSet K;
     K.n = in.n_kinds;
     if (K.n < 1 || K.n > TSFX_MAX_KINDS) return fail(ctx, TSFX_E_INVALID, "between 1 and 64 kinds per call");
-    bool any_times = false;
     for (int k = 0; k < K.n; ++k) {
         if (!plans[k] || plans[k]->ctx != ctx) return fail(ctx, TSFX_E_INVALID, "plan does not belong to this context");
         K.plan[k] = plans[k];
         K.col0[k] = K.total_cols;
         K.total_cols += plans[k]->ncols;
-        any_times = any_times || plans[k]->need_times;
     }
     for (int k = 0; k < K.n; ++k) if (plans[k]->need_times) plan = plans[k];      // take_times looks at one plan's flag
     const size_t kstride = kind_stride(in.n);
@@ -1251,9 +1249,12 @@ static int extract_long_impl(tsfx_ctx* ctx, const tsfx_plan* const* plans, const
         if (rc) return rc;
         if (out_ids) CK(cudaMemcpyAsync(out_ids, W.d_uid, (size_t)ns * sizeof(int64_t), in.device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         if (in.device && !first_sorted_try) break;                       // asynchronous contract: nothing to wait for
-        if (first_sorted_try) CK(cudaMemcpyAsync(W.h_info, W.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        // the NaN scans of the other kinds' columns were queued after the sort pass read its flags: read them again
+        const bool late_nan_flags = !first_sorted_try && K.n > 1 && check_nan;
+        if (first_sorted_try || late_nan_flags) CK(cudaMemcpyAsync(W.h_info, W.d_info, sizeof(CsrInfo), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->s_out));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (late_nan_flags && W.h_info->has_nan) return nan_error(ctx);
         if (!first_sorted_try) break;
         if (W.h_info->has_nan) return nan_error(ctx);
         if (!W.h_info->unsorted_keys) break;
