@@ -152,3 +152,23 @@ def test_pinned_pool_reuses_blocks(env):
     gc.collect()
     b = ctx.pinned_array(shape, np.float64)
     assert b.ctypes.data == addr                          # the freed block came back from the pool
+
+
+def test_nan_in_a_later_kind_of_a_shuffled_wide_frame(env):
+    """wide frame, rows out of order (device sort): the NaN scan of the second kind's column runs after the sort pass
+    read its flags; the call must still fail with the reference's error"""
+    from tsfresh_b200 import _lib
+    ctx, dp, plan = env
+    rng = np.random.default_rng(8)
+    ids, t, v, lens = frame(3_000, rng)
+    w = rng.standard_normal(len(v)).astype(np.float32)
+    perm = rng.permutation(len(ids))
+    uid, mat = _lib.extract_long_kinds(ctx, [dp, dp], ids[perm], t[perm], [v[perm], w[perm]])
+    uid_ref, ref = dense_reference(dp, ids, t, v)
+    assert np.array_equal(uid, uid_ref) and np.array_equal(mat[:, :plan.n_cols], ref, equal_nan=True)
+    assert np.array_equal(mat[:, plan.n_cols:], dense_reference(dp, ids, t, w)[1], equal_nan=True)
+    w[len(w) // 3] = np.nan
+    with pytest.raises(ValueError, match="contains NaN"):
+        _lib.extract_long_kinds(ctx, [dp, dp], ids[perm], t[perm], [v[perm], w[perm]])
+    with pytest.raises(ValueError, match="contains NaN"):
+        _lib.extract_long_kinds(ctx, [dp, dp], ids, t, [v, w])                  # ordered rows: caught while streaming
