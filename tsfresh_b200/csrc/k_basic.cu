@@ -4,8 +4,10 @@
 // xc[nxc] float64 (centred copy x - mean with a zero tail for the tiled lag products), scr[nscr] float64
 // (scratch: chunk aggregates, histograms, cumulative masses, peak radii), lagS[nlag] float64 (lag products, pacf),
 // ST[32] (shared statistics read by the lane-parallel finishers), altS[6 nalt] (regression sums per
-// agg_linear_trend key).  Calculators restated (feature_calculators.py line numbers in
-// include/tsfx.h): every "class M" and "class O" row of SURVEY.md section 8a.
+// agg_linear_trend key); in front of the per-warp regions one CTA-wide copy of the descriptor table.  Two CTAs of 12
+// warps per SM walk the descriptor list in lock step (instruction-cache sharing); the 41 lag products run on the FP64
+// tensor cores (lag_products_dmma).  Calculators restated (feature_calculators.py line numbers in
+// include/tsfx.h): every "class M" and "class O" row of SURVEY.md section 8a, plus linear_trend_timewise.
 #include "tsfx_common.cuh"
 #include "tsfx_math.cuh"
 #include "tsfx_kernels.h"

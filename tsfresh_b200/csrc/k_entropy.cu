@@ -5,9 +5,11 @@
 // Chebyshev distance is <= tau, for templates of length 2 (i, j in [0, n-2]) and of length 3
 // (i, j in [0, n-3]).  One warp per series; up to NT = 6 tolerances share one pass so the distances are formed
 // once.  Differences are float64 of float32-origin values, i.e. the very same IEEE operations numpy performs,
-// so the counts are bit-identical to the reference's.  Two formulations of the counting:
-//   * bit tiles (default, entropy_bittile): lane = row i, 32-column bit words per tolerance, counts by popcount
-//     of three shifted rows -- ~17 warp instructions per 32 pair tests and 6 tolerances;
+// so the counts are bit-identical to the reference's.  Three formulations of the counting (TSFX_ENTROPY selects):
+//   * rank space (default, k_entropy_rank; series of up to ~1100 samples): sort once, the matches of a sample are a
+//     contiguous rank interval, bit rows come from a prefix-bit table -- no pair tests at all (see the comment there);
+//   * bit tiles (TSFX_ENTROPY=tiles and all longer series, entropy_bittile): lane = row i, 32-column bit words per
+//     tolerance, counts by popcount of three shifted rows -- ~17 warp instructions per 32 pair tests and 6 tolerances;
 //   * pair sweep (TSFX_ENTROPY=pairs, entropy_sweep): lane = row i, sequential sweep over j with the three
 //     neighbouring samples in registers -- ~35; kept for A/B measurements and as a cross-check.
 #include <algorithm>

@@ -3,9 +3,13 @@
 //   permutation_entropy   (feature_calculators.py:1866-1915)   rank codes -> bitonic sort -> run lengths
 //   number_cwt_peaks      (feature_calculators.py:1320-1339; scipy.signal.find_peaks_cwt with _ricker :1307)
 //
-// One warp per series.  Shared memory per warp (doubles first): row0[npad], tmp[npad] (cwt rows),
-// hw[TSFX_MAXW_PTS] (wavelet taps), then uint32 codes[npow2], uint16 trie[LZ_LANES][3][npad+1],
-// uint32 maxbits[TSFX_CWT_MAXN][npad/32+1], int16 line tables [5][2*npad], float xs[npad].
+// One warp per series.  k_seq (lempel_ziv + permutation_entropy): general layout = uint32 codes[npow2], one uint32
+// open-addressing key table per Lempel-Ziv parameter, uint16 symbols, float xs[npad] (17.8 KB per warp at 256 samples,
+// run from the global working region); compact layout k_seq_small (series <= 256, alphabets <= 127) = packed 16-bit
+// histogram counters, 16-bit keys in 256-slot tables, byte symbols (6.5 KB per warp, shared memory, 32 warps per SM).
+// k_peaks (number_cwt_peaks): row0[npad], tmp[npad] (cwt rows, float64), noise[npad], hw[TSFX_MAXW_PTS] (wavelet taps),
+// float32 copies of the wider rows, a zero-padded float64 copy of the series in the working region; the ridge-line
+// tables (5 int16 + 3 int32 per line), the column map and the local-maximum bit masks in shared memory.
 #include <algorithm>
 
 #include "tsfx_common.cuh"

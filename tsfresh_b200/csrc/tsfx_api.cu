@@ -1,4 +1,6 @@
-// tsfx_api.cu -- the C ABI of libtsfx.so (include/tsfx.h): context, plan, extraction entry points.
+// tsfx_api.cu -- the C ABI of libtsfx.so (include/tsfx.h): context, plan, extraction entry points, and the native
+// runtime around the kernels: pinned host pool, threaded pageable->pinned staging ring, the row-block pipeline of the
+// long-frame path (stage (a) + kernels + result transfer on three streams), multi-GPU result placement.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
